@@ -1,0 +1,391 @@
+// api.cu - the extern "C" boundary declared in include/cm3env.h.
+// Handles hold configuration only; every buffer is the caller's (see the header).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "params.cuh"
+
+namespace cm3 {
+
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+        set_error("%s: %s - this library has no CPU fallback", what, cudaGetErrorString(e));
+        return CM3_ERR_NO_DEVICE;
+    }
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return CM3_ERR_CUDA;
+}
+
+static int require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device visible (%s) - this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return CM3_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (0..%d)", device, n - 1);
+        return CM3_ERR_BAD_ARG;
+    }
+    return CM3_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static size_t real_size(int real) { return real == CM3_REAL_F64 ? 8 : 4; }
+
+}  // namespace cm3
+
+using namespace cm3;
+
+struct cm3_checkers_s {
+    cm3_checkers_config cfg;
+    CkParams base;  // geometry-derived constants, pointers zero
+};
+struct cm3_particle_s {
+    cm3_particle_config cfg;
+    PtParams base;
+};
+
+extern "C" {
+
+int cm3_abi_version(void) { return CM3_ABI_VERSION; }
+const char *cm3_last_error(void) { return g_last_error; }
+
+int cm3_device_count(int *count) {
+    if (!count) { set_error("count is NULL"); return CM3_ERR_BAD_ARG; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    *count = n;
+    return CM3_OK;
+}
+
+/* ------------------------------------------------------------------ Checkers */
+
+int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out) {
+    if (!cfg || !out) { set_error("cfg/out is NULL"); return CM3_ERR_BAD_ARG; }
+    *out = nullptr;
+    const int R = cfg->n_rows, C = cfg->n_columns, O = cfg->n_obs, N = cfg->n_agents;
+    // the reference's own asserts, env/checkers.py:16-17
+    if (R < 1 || C < 2 || R % 2 != 1 || C % 2 != 0) {
+        set_error("n_rows must be odd and n_columns even (got %d, %d)", R, C);
+        return CM3_ERR_BAD_SHAPE;
+    }
+    if (O < 1 || N < 1 || cfg->num_envs < 1 || cfg->max_steps < 0 || cfg->max_steps > 0xFFFFFF ||
+        (cfg->real != CM3_REAL_F32 && cfg->real != CM3_REAL_F64)) {
+        set_error("bad n_obs/n_agents/num_envs/max_steps/real");
+        return CM3_ERR_BAD_ARG;
+    }
+    if (N > CM3_MAX_AGENTS || !checkers_geometry_supported(R, C, O, N)) {
+        set_error("no compiled Checkers kernel for n_rows=%d n_columns=%d n_obs=%d n_agents=%d", R, C, O, N);
+        return CM3_ERR_UNSUPPORTED;
+    }
+    if (N == 1 && R < 3) {  // checkers.py:276 starts the agent on row 2
+        set_error("n_agents == 1 needs n_rows >= 3 (checkers.py:276)");
+        return CM3_ERR_BAD_SHAPE;
+    }
+    for (int i = 0; i < N; ++i) {
+        // bitboard occupancy == the reference's world[..,2] only while agents stand on distinct
+        // cells of the valid grid; the reference configs all satisfy this
+        if (cfg->agents_r[i] < 0 || cfg->agents_r[i] >= R || cfg->agents_c[i] < 0 || cfg->agents_c[i] > C) {
+            set_error("agent %d starts outside the valid grid", i);
+            return CM3_ERR_BAD_ARG;
+        }
+        for (int j = 0; j < i; ++j)
+            if (N > 1 && cfg->agents_r[i] == cfg->agents_r[j] && cfg->agents_c[i] == cfg->agents_c[j]) {
+                set_error("agents %d and %d start on the same cell", j, i);
+                return CM3_ERR_BAD_ARG;
+            }
+    }
+    int st = require_device(cfg->device);
+    if (st != CM3_OK) return st;
+
+    cm3_checkers_s *h = new (std::nothrow) cm3_checkers_s();
+    if (!h) { set_error("out of host memory"); return CM3_ERR_BAD_ARG; }
+    h->cfg = *cfg;
+    CkParams &p = h->base;
+    memset(&p, 0, sizeof(p));
+    p.B = cfg->num_envs;
+    p.max_steps = cfg->max_steps;
+    p.env_id_offset = cfg->env_id_offset;
+    const int TR = R + 2 * O, TC = C + 2 * O + 1;  // checkers.py:24-25
+    for (int i = 0; i < N; ++i) {
+        p.start_r[i] = cfg->agents_r[i] + O;  // checkers.py:34-35
+        p.start_c[i] = cfg->agents_c[i] + O;
+    }
+    // normalize(), checkers.py:120-121, and collected/(max_collectible/2.0), :139 - same
+    // float64 expressions as the reference, tabulated over every reachable integer
+    for (int r = 0; r < TR; ++r) p.norm_row[r] = ((double)r - TR / 2.0) / TR;
+    for (int c = 0; c < TC; ++c) p.norm_col[c] = ((double)c - TC / 2.0) / TC;
+    const int max_collectible = R * C;
+    for (int k = 0; k <= max_collectible / 2; ++k) p.norm_cnt[k] = (double)k / (max_collectible / 2.0);
+    *out = h;
+    return CM3_OK;
+}
+
+int cm3_checkers_destroy(cm3_checkers_t h) {
+    if (!h) { set_error("handle is NULL"); return CM3_ERR_BAD_ARG; }
+    delete h;
+    return CM3_OK;
+}
+
+static int ck_fill(cm3_checkers_t h, const cm3_checkers_state *st, const cm3_checkers_outputs *outs,
+                   CkParams &p) {
+    if (!h || !st || !st->remaining || !st->agents || !st->meta) {
+        set_error("handle/state pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    p = h->base;
+    p.remaining = st->remaining; p.agents = st->agents; p.meta = st->meta;
+    if (outs) {
+        p.grid = (char *)outs->grid; p.vec = (char *)outs->vec; p.obs_others = (char *)outs->obs_others;
+        p.obs_self_t = (char *)outs->obs_self_t; p.obs_self_v = (char *)outs->obs_self_v;
+        p.reward = (char *)outs->reward; p.local_rewards = (char *)outs->local_rewards;
+        p.done = outs->done;
+    }
+    return CM3_OK;
+}
+
+static int ck_launch(cm3_checkers_t h, const CkParams &p, void *stream) {
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    return checkers_launch(h->cfg.n_rows, h->cfg.n_columns, h->cfg.n_obs, h->cfg.n_agents, h->cfg.real, p,
+                           (cudaStream_t)stream);
+}
+
+int cm3_checkers_reset(cm3_checkers_t h, const cm3_checkers_state *st, const uint8_t *goal_idx,
+                       const uint8_t *env_mask, const cm3_checkers_outputs *outs, void *stream) {
+    CkParams p;
+    int rc = ck_fill(h, st, outs, p);
+    if (rc != CM3_OK) return rc;
+    p.mode = 1; p.T = 1;
+    p.goal_idx = goal_idx; p.env_mask = env_mask;
+    p.reward = nullptr; p.local_rewards = nullptr;
+    return ck_launch(h, p, stream);
+}
+
+int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                         uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset, int8_t *actions_out,
+                         const cm3_checkers_outputs *outs, void *stream) {
+    CkParams p;
+    int rc = ck_fill(h, st, outs, p);
+    if (rc != CM3_OK) return rc;
+    if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
+    p.actions = actions; p.actions_out = actions_out;
+    p.seed = seed; p.t0 = t0;
+    return ck_launch(h, p, stream);
+}
+
+int cm3_checkers_step(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                      const cm3_checkers_outputs *outs, void *stream) {
+    if (!actions) { set_error("actions is NULL"); return CM3_ERR_BAD_ARG; }
+    return cm3_checkers_rollout(h, st, actions, 0, 0, 1, 0, nullptr, outs, stream);
+}
+
+int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
+                           int8_t *actions_dev, const cm3_checkers_outputs *od,
+                           const cm3_checkers_outputs *oh, void *stream) {
+    if (!h || !actions_host || !actions_dev || !od || !oh) {
+        set_error("handle/actions/outputs pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
+    const size_t W = 2 * h->cfg.n_obs + 1, L = 2 * (N > 1 ? N - 1 : 1);
+    CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
+    int rc = cm3_checkers_step(h, st, actions_dev, od, stream);
+    if (rc != CM3_OK) return rc;
+    struct { void *dst; const void *src; size_t bytes; } cp[] = {
+        {oh->grid, od->grid, B * h->cfg.n_rows * (h->cfg.n_columns + 1) * 2 * rs},
+        {oh->vec, od->vec, B * N * 4 * rs},
+        {oh->obs_others, od->obs_others, B * N * L * rs},
+        {oh->obs_self_t, od->obs_self_t, B * N * W * W * 3 * rs},
+        {oh->obs_self_v, od->obs_self_v, B * N * 4 * rs},
+        {oh->reward, od->reward, B * rs},
+        {oh->local_rewards, od->local_rewards, B * N * rs},
+        {oh->done, od->done, B},
+    };
+    for (auto &c : cp) {
+        if (!c.dst) continue;
+        if (!c.src) { set_error("host output requested for a field with no device buffer"); return CM3_ERR_BAD_ARG; }
+        CM3_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CM3_CUDA(cudaStreamSynchronize(s));
+    return CM3_OK;
+}
+
+/* ------------------------------------------------------------------ Particle */
+
+void cm3_particle_default_config(cm3_particle_config *cfg, int32_t n_agents, int32_t max_steps) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->n_agents = n_agents;
+    cfg->max_steps = max_steps;
+    cfg->num_envs = 1;
+    cfg->real = CM3_REAL_F32;
+    cfg->dt = 0.1;              /* core.py:94 */
+    cfg->damping = 0.25;        /* core.py:96 */
+    cfg->contact_force = 1e+2;  /* core.py:98 */
+    cfg->contact_margin = 1e-3; /* core.py:99 */
+    cfg->agent_size = 0.15;     /* multi-goal_spread.py:47 */
+    cfg->mass = 1.0;            /* core.py:47-51 */
+    cfg->sensitivity = 5.0;     /* environment.py:211 */
+    cfg->reach_thresh = 0.05;   /* multi-goal_spread.py:126 */
+}
+
+int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
+    if (!cfg || !out) { set_error("cfg/out is NULL"); return CM3_ERR_BAD_ARG; }
+    *out = nullptr;
+    if (cfg->n_agents < 1 || cfg->num_envs < 1 || cfg->max_steps < 0 ||
+        (cfg->real != CM3_REAL_F32 && cfg->real != CM3_REAL_F64)) {
+        set_error("bad n_agents/num_envs/max_steps/real");
+        return CM3_ERR_BAD_ARG;
+    }
+    if (cfg->n_agents > CM3_MAX_AGENTS) {
+        set_error("no compiled particle kernel for n_agents=%d (1..%d supported)", cfg->n_agents, CM3_MAX_AGENTS);
+        return CM3_ERR_UNSUPPORTED;
+    }
+    int st = require_device(cfg->device);
+    if (st != CM3_OK) return st;
+    cm3_particle_s *h = new (std::nothrow) cm3_particle_s();
+    if (!h) { set_error("out of host memory"); return CM3_ERR_BAD_ARG; }
+    h->cfg = *cfg;
+    PtParams &p = h->base;
+    memset(&p, 0, sizeof(p));
+    p.B = cfg->num_envs; p.max_steps = cfg->max_steps; p.env_id_offset = cfg->env_id_offset;
+    p.dt = cfg->dt; p.damping = cfg->damping; p.contact_force = cfg->contact_force;
+    p.contact_margin = cfg->contact_margin;
+    p.dist_min = cfg->agent_size + cfg->agent_size;  // core.py:189 / multi-goal_spread.py:117
+    p.mass = cfg->mass; p.sensitivity = cfg->sensitivity; p.reach_thresh = cfg->reach_thresh;
+    for (int i = 0; i < CM3_MAX_AGENTS; ++i) {
+        p.agents_x[i] = cfg->agents_x[i]; p.agents_y[i] = cfg->agents_y[i];
+        p.landmarks_x[i] = cfg->landmarks_x[i]; p.landmarks_y[i] = cfg->landmarks_y[i];
+    }
+    p.initial_std = cfg->initial_std; p.prob_random = cfg->prob_random;
+    *out = h;
+    return CM3_OK;
+}
+
+int cm3_particle_destroy(cm3_particle_t h) {
+    if (!h) { set_error("handle is NULL"); return CM3_ERR_BAD_ARG; }
+    delete h;
+    return CM3_OK;
+}
+
+static int pt_fill(cm3_particle_t h, const cm3_particle_state *st, const cm3_particle_outputs *outs,
+                   PtParams &p) {
+    if (!h || !st || !st->sv || !st->landmarks || !st->steps || !st->collisions || !st->reached) {
+        set_error("handle/state pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    p = h->base;
+    p.sv = (char *)st->sv; p.landmarks = (char *)st->landmarks;
+    p.steps = st->steps; p.collisions = st->collisions; p.reached = st->reached;
+    if (outs) {
+        p.global_state = (char *)outs->global_state; p.obs_others = (char *)outs->obs_others;
+        p.obs_self = (char *)outs->obs_self; p.reward = (char *)outs->reward;
+        p.reward_n = (char *)outs->reward_n; p.done = outs->done;
+    }
+    return CM3_OK;
+}
+
+static int pt_launch(cm3_particle_t h, const PtParams &p, void *stream) {
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    return particle_launch(h->cfg.n_agents, h->cfg.real, p, (cudaStream_t)stream);
+}
+
+int cm3_particle_reset(cm3_particle_t h, const cm3_particle_state *st, const void *init_pos,
+                       const void *init_landmarks, const uint8_t *env_mask, uint64_t seed,
+                       int64_t reset_counter, const cm3_particle_outputs *outs, void *stream) {
+    PtParams p;
+    int rc = pt_fill(h, st, outs, p);
+    if (rc != CM3_OK) return rc;
+    if ((init_pos == nullptr) != (init_landmarks == nullptr)) {
+        set_error("init_pos and init_landmarks must be given together");
+        return CM3_ERR_BAD_ARG;
+    }
+    p.mode = 1; p.T = 1;
+    p.init_pos = (const char *)init_pos; p.init_landmarks = (const char *)init_landmarks;
+    p.env_mask = env_mask; p.seed = seed; p.reset_counter = reset_counter;
+    p.reward = nullptr; p.reward_n = nullptr;
+    return pt_launch(h, p, stream);
+}
+
+int cm3_particle_rollout(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                         uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset, int8_t *actions_out,
+                         const cm3_particle_outputs *outs, void *stream) {
+    PtParams p;
+    int rc = pt_fill(h, st, outs, p);
+    if (rc != CM3_OK) return rc;
+    if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
+    p.actions = actions; p.actions_out = actions_out; p.seed = seed; p.t0 = t0;
+    return pt_launch(h, p, stream);
+}
+
+int cm3_particle_step(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                      const cm3_particle_outputs *outs, void *stream) {
+    if (!actions) { set_error("actions is NULL"); return CM3_ERR_BAD_ARG; }
+    return cm3_particle_rollout(h, st, actions, 0, 0, 1, 0, nullptr, outs, stream);
+}
+
+int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
+                           int8_t *actions_dev, const cm3_particle_outputs *od,
+                           const cm3_particle_outputs *oh, void *stream) {
+    if (!h || !actions_host || !actions_dev || !od || !oh) {
+        set_error("handle/actions/outputs pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
+    const size_t LO = 4 * (N > 1 ? N - 1 : 1);
+    CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
+    int rc = cm3_particle_step(h, st, actions_dev, od, stream);
+    if (rc != CM3_OK) return rc;
+    struct { void *dst; const void *src; size_t bytes; } cp[] = {
+        {oh->global_state, od->global_state, B * N * 4 * rs},
+        {oh->obs_others, od->obs_others, B * N * LO * rs},
+        {oh->obs_self, od->obs_self, B * N * 4 * rs},
+        {oh->reward, od->reward, B * rs},
+        {oh->reward_n, od->reward_n, B * N * rs},
+        {oh->done, od->done, B},
+    };
+    for (auto &c : cp) {
+        if (!c.dst) continue;
+        if (!c.src) { set_error("host output requested for a field with no device buffer"); return CM3_ERR_BAD_ARG; }
+        CM3_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CM3_CUDA(cudaStreamSynchronize(s));
+    return CM3_OK;
+}
+
+}  // extern "C"

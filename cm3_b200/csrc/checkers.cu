@@ -1,0 +1,425 @@
+// checkers.cu - fused Checkers reset/step/rollout kernel for sm_100a.
+//
+// What it computes: env/checkers.py of the reference - agent_act (:157-187), get_reward
+// (:190-225), step (:228-262), reset + populate_world (:265-291, :38-63), get_global_state
+// (:79-94) and get_local_observation (:128-154) - for B env instances at once.
+//
+// Design:
+//  * state is compact: a bitboard of the cells that still hold a reward, packed agent words
+//    and a step/goal word - 8 + 4N + 4 bytes per env; the dense [rows][cols][3] float world of
+//    the reference is never materialised;
+//  * one lane per (env, agent): a warp owns EW = 32/N consecutive envs.  Every lane replays the
+//    (sequential, order-dependent) N-agent move/collect update of its env redundantly in
+//    registers - it is ~40 instructions per agent - so no lane waits for another;
+//  * the two bulky outputs (the per-agent (2O+1)^2 x 3 window and the R x (C+1) x 2 grid, 90 % of
+//    the bytes) are expanded from bit patterns into a per-warp shared-memory tile whose layout is
+//    exactly the layout of the output arrays for those EW envs, and leave the SM as ONE TMA bulk
+//    store per field (cp.async.bulk.global.shared::cta) - full-line HBM writes with no store
+//    instructions spent on them.  The lane->(env,agent) mapping is agent-major so that for N = 2
+//    the two half-warps hit odd/even banks: the staging stores are conflict free;
+//  * the small per-agent vectors are written straight from registers: consecutive lanes write
+//    consecutive 16-byte records;
+//  * T steps can be fused in one launch (rollout): state stays in registers, actions come from
+//    an int8 stream or from Philox4x32-10, and finished episodes can be reset in-kernel.
+#include "common.cuh"
+#include "params.cuh"
+
+namespace cm3 {
+
+constexpr int kCkWarpsPerBlock = 2;
+
+template <typename Real> __device__ __forceinline__ Real tri_value(uint32_t nz, uint32_t neg);
+// value in {0, +1, -1}: nz = cell is non-zero, neg = cell is -1 (neg implies nz)
+template <> __device__ __forceinline__ float tri_value<float>(uint32_t nz, uint32_t neg) {
+    return __uint_as_float(nz * 0x3F800000u | (neg << 31));
+}
+template <> __device__ __forceinline__ double tri_value<double>(uint32_t nz, uint32_t neg) {
+    return (double)((int)nz - 2 * (int)neg);
+}
+
+template <typename Real> __device__ __forceinline__ void store4(Real *p, Real a, Real b, Real c, Real d);
+template <> __device__ __forceinline__ void store4<float>(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<double>(double *p, double a, double b, double c, double d) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
+}
+template <typename Real> __device__ __forceinline__ void store2(Real *p, Real a, Real b);
+template <> __device__ __forceinline__ void store2<float>(float *p, float a, float b) {
+    *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+}
+template <> __device__ __forceinline__ void store2<double>(double *p, double a, double b) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+}
+
+template <int N> __device__ __forceinline__ int pick(const int (&v)[N], int idx) {
+    int r = v[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) r = (idx == i) ? v[i] : r;
+    return r;
+}
+
+template <int R, int C, int O, int N, typename Real>
+struct CkGeom {
+    static constexpr int TR = R + 2 * O;
+    static constexpr int TC = C + 2 * O + 1;
+    static constexpr int W = 2 * O + 1;
+    static constexpr int WW3 = W * W * 3;
+    static constexpr int G = R * (C + 1) * 2;
+    static constexpr int L = 2 * (N > 1 ? N - 1 : 1);
+    static constexpr int NP = (N == 3) ? 4 : N;  // lanes reserved per env
+    static constexpr int EW = kWarp / NP;        // envs per warp
+    static constexpr int CNT = R * C / 2 + 1;
+    static constexpr int kWinBytes = round_up(EW * N * WW3 * (int)sizeof(Real), 16);
+    static constexpr int kGridBytes = round_up(EW * G * (int)sizeof(Real), 16);
+    static constexpr int kWarpStageBytes = kWinBytes + kGridBytes;
+    static constexpr int kLutBytes = round_up((TR + TC + CNT) * (int)sizeof(Real), 128);
+    static constexpr int kSmemBytes = kLutBytes + kCkWarpsPerBlock * kWarpStageBytes;
+    static constexpr uint32_t CM = (C >= 32) ? 0xFFFFFFFFu : ((1u << C) - 1u);
+    static constexpr uint32_t kEven = 0x55555555u & CM;  // columns j with j even
+    static constexpr uint32_t kOdd = 0xAAAAAAAAu & CM;
+    static constexpr uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
+    static_assert(R % 2 == 1 && C % 2 == 0, "checkers.py:16-17");
+    static_assert(R * C <= 64 && TC <= 32 && TR <= kCkMaxTR && N >= 1 && N <= CM3_MAX_AGENTS, "geometry");
+
+    // cells (i,j) with (i+j) even are green, odd orange (checkers.py:54-63)
+    static __host__ __device__ constexpr uint64_t color_all(int color) {
+        uint64_t m = 0;
+        for (int i = 0; i < R; ++i)
+            for (int j = 0; j < C; ++j)
+                if (((i + j) & 1) == color) m |= 1ull << (i * C + j);
+        return m;
+    }
+};
+
+template <int R, int C, int O, int N, typename Real>
+__global__ void __launch_bounds__(kCkWarpsPerBlock *kWarp)
+checkers_kernel(const __grid_constant__ CkParams p) {
+    using Gm = CkGeom<R, C, O, N, Real>;
+    constexpr int TR = Gm::TR, TC = Gm::TC, W = Gm::W, WW3 = Gm::WW3, G = Gm::G, L = Gm::L;
+    constexpr int EW = Gm::EW;
+    constexpr uint32_t CM = Gm::CM;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Real *lut_row = reinterpret_cast<Real *>(smem_raw);
+    Real *lut_col = lut_row + TR;
+    Real *lut_cnt = lut_col + TC;
+    for (int i = threadIdx.x; i < TR; i += blockDim.x) lut_row[i] = (Real)p.norm_row[i];
+    for (int i = threadIdx.x; i < TC; i += blockDim.x) lut_col[i] = (Real)p.norm_col[i];
+    for (int i = threadIdx.x; i < Gm::CNT; i += blockDim.x) lut_cnt[i] = (Real)p.norm_cnt[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Real *stage_win = reinterpret_cast<Real *>(smem_raw + Gm::kLutBytes + warp * Gm::kWarpStageBytes);
+    Real *stage_grid = reinterpret_cast<Real *>(reinterpret_cast<unsigned char *>(stage_win) + Gm::kWinBytes);
+
+    const int tile = blockIdx.x * kCkWarpsPerBlock + warp;
+    const int env0 = tile * EW;
+    if (env0 >= p.B) return;  // warp-uniform; no block-level sync below this point
+    const int a = lane / EW, e = lane % EW;  // agent-major: lanes [a*EW, (a+1)*EW) hold agent a
+    const int env = env0 + e;
+    const int nenv = min(EW, p.B - env0);
+    const bool valid = (a < N) && (e < nenv);
+    const size_t B = (size_t)p.B;
+
+    // ---- load compact state
+    uint64_t rem = 0;
+    int ar[N], ac[N], ng[N], no[N];
+    uint32_t meta = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { ar[i] = O; ac[i] = O + i; ng[i] = 0; no[i] = 0; }
+    if (valid) {
+        rem = p.remaining[env];
+        meta = p.meta[env];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t w = p.agents[(size_t)env * N + i];
+            ar[i] = w & 0xFF; ac[i] = (w >> 8) & 0xFF; ng[i] = (w >> 16) & 0xFF; no[i] = w >> 24;
+        }
+    }
+    int steps = meta & 0xFFFFFF;
+    uint32_t goals = meta >> 24;
+
+    auto reset_state = [&]() {
+        rem = Gm::kFull;
+        steps = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ar[i] = p.start_r[i]; ac[i] = p.start_c[i]; ng[i] = 0; no[i] = 0;
+        }
+        if (N == 1) ar[0] = ((goals & 1) ? 2 : 0) + O;  // checkers.py:271-276
+    };
+
+    bool pending = false;  // bulk stores of this warp whose smem source may still be in flight
+
+    // Expands the observations of the current state into the outputs of time slot t.
+    auto emit = [&](int t) {
+        const size_t slot = (size_t)t * B;
+        const int my_r = pick<N>(ar, a), my_c = pick<N>(ac, a);
+        if (pending) {
+            if (lane < 2) bulk_wait_read();
+        }
+        __syncwarp();
+        // ---------------- window of agent a (get_obs, checkers.py:97-109)
+        if (p.obs_self_t != nullptr && valid) {
+            Real *win = stage_win + (e * N + a) * WW3;
+            const int sh = my_c - O;  // leftmost window column, >= 0
+#pragma unroll
+            for (int dr = 0; dr < W; ++dr) {
+                const int pr = my_r - O + dr;  // expanded row
+                const int i = pr - O;          // valid-grid row
+                const bool inr = (unsigned)i < (unsigned)R;
+                const uint32_t rowrem = inr ? ((uint32_t)(rem >> (inr ? i * C : 0)) & CM) : 0u;
+                const uint32_t gmask = (i & 1) ? Gm::kOdd : Gm::kEven;
+                const uint32_t omask = CM & ~gmask;
+                uint32_t occ = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) occ |= (ar[k] == pr) ? (1u << ac[k]) : 0u;
+                if (dr == O) occ &= ~(1u << my_c);  // own cell reads as free, :107
+                // patterns over expanded columns, then cut to the W window columns
+                const uint32_t border = inr ? (((1u << O) - 1u) | (~0u << (O + C + 1))) : ~0u;
+                const uint32_t nz0 = (inr ? (gmask << O) : 0u) >> sh;
+                const uint32_t ng0 = ((rowrem & gmask) << O) >> sh;
+                const uint32_t nz1 = (inr ? (omask << O) : 0u) >> sh;
+                const uint32_t ng1 = ((rowrem & omask) << O) >> sh;
+                const uint32_t nz2 = (border | occ) >> sh;
+                const uint32_t ng2 = occ >> sh;
+#pragma unroll
+                for (int dc = 0; dc < W; ++dc) {
+                    Real *cell = win + (dr * W + dc) * 3;
+                    cell[0] = tri_value<Real>((nz0 >> dc) & 1u, (ng0 >> dc) & 1u);
+                    cell[1] = tri_value<Real>((nz1 >> dc) & 1u, (ng1 >> dc) & 1u);
+                    cell[2] = tri_value<Real>((nz2 >> dc) & 1u, (ng2 >> dc) & 1u);
+                }
+            }
+        }
+        // ---------------- global grid (get_valid_grid, :66-76): lane a writes channel a
+        if (p.grid != nullptr && valid && a < 2) {
+            Real *gr = stage_grid + e * G;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const uint32_t rowrem = (uint32_t)(rem >> (i * C)) & CM;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    if (N > 1 && ch == 1) break;           // N > 1: one channel per lane
+                    const int mych = (N > 1) ? a : ch;
+                    const uint32_t cmask = (((i & 1) ^ mych) ? Gm::kOdd : Gm::kEven);
+                    const uint32_t neg = rowrem & cmask;
+#pragma unroll
+                    for (int j = 0; j <= C; ++j) {
+                        const uint32_t nzb = (j < C) ? ((cmask >> j) & 1u) : 0u;
+                        const uint32_t ngb = (j < C) ? ((neg >> j) & 1u) : 0u;
+                        gr[(i * (C + 1) + j) * 2 + mych] = tri_value<Real>(nzb, ngb);
+                    }
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        pending = false;
+        if (p.obs_self_t != nullptr) {
+            Real *g = reinterpret_cast<Real *>(p.obs_self_t) + (slot + env0) * (size_t)(N * WW3);
+            const uint32_t bytes = (uint32_t)(nenv * N * WW3 * sizeof(Real));
+            if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
+                if (lane == 0) { bulk_store(g, stage_win, bytes); bulk_commit(); }
+                pending = true;
+            } else {
+                for (int idx = lane; idx < nenv * N * WW3; idx += kWarp) g[idx] = stage_win[idx];
+            }
+        }
+        if (p.grid != nullptr) {
+            Real *g = reinterpret_cast<Real *>(p.grid) + (slot + env0) * (size_t)G;
+            const uint32_t bytes = (uint32_t)(nenv * G * sizeof(Real));
+            if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
+                if (lane == 1) { bulk_store(g, stage_grid, bytes); bulk_commit(); }
+                pending = true;
+            } else {
+                for (int idx = lane; idx < nenv * G; idx += kWarp) g[idx] = stage_grid[idx];
+            }
+        }
+        // ---------------- small per-agent vectors, straight from registers
+        if (valid) {
+            const size_t rec = (slot + env) * N + a;
+            const int my_g = pick<N>(ng, a), my_o = pick<N>(no, a);
+            if (p.vec != nullptr)  // get_global_state, :89-93
+                store4<Real>(reinterpret_cast<Real *>(p.vec) + rec * 4, (Real)my_r, (Real)my_c, (Real)my_g, (Real)my_o);
+            if (p.obs_self_v != nullptr)  // :137-139
+                store4<Real>(reinterpret_cast<Real *>(p.obs_self_v) + rec * 4, lut_row[my_r], lut_col[my_c],
+                             lut_cnt[my_g], lut_cnt[my_o]);
+            if (p.obs_others != nullptr) {  // :143-151
+                Real *oo = reinterpret_cast<Real *>(p.obs_others) + rec * L;
+                if (N == 1) {
+                    store2<Real>(oo, lut_row[my_r], lut_col[my_c]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < N - 1; ++k) {
+                        const int j = k + (k >= a ? 1 : 0);
+                        store2<Real>(oo + 2 * k, lut_row[pick<N>(ar, j)], lut_col[pick<N>(ac, j)]);
+                    }
+                }
+            }
+        }
+    };
+
+    const int T_eff = (p.mode == kCkReset) ? 1 : p.T;
+    for (int t = 0; t < T_eff; ++t) {
+        bool sel = false;
+        if (p.mode == kCkReset) {
+            sel = valid && (p.env_mask == nullptr || p.env_mask[env] != 0);
+            if (sel) {
+                goals = 0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const uint32_t g = p.goal_idx ? (p.goal_idx[(size_t)env * N + i] & 1u) : (uint32_t)(i & 1);
+                    goals |= g << i;
+                }
+                reset_state();
+            }
+        } else {
+            // ---- actions of all agents of my env
+            int act[N];
+            if (p.actions != nullptr) {
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    act[i] = valid ? (int)p.actions[((size_t)t * B + env) * N + i] : 0;
+            } else {
+                const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env),
+                                                      (uint64_t)(p.t0 + t));
+#pragma unroll
+                for (int i = 0; i < N; ++i) act[i] = action_from_word(philox_word(w, i), 5);
+            }
+            if (p.actions_out != nullptr && valid)
+                p.actions_out[((size_t)t * B + env) * N + a] = (int8_t)pick<N>(act, a);
+
+            // ---- agents act and collect strictly in index order (checkers.py:233-237)
+            double rew[N];
+            double total = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int ai = act[i];
+                const int tr = ar[i] + (ai == 2) - (ai == 1);
+                const int tc = ac[i] + (ai == 4) - (ai == 3);
+                const bool wants = (unsigned)(ai - 1) < 4u;
+                // world[..,2] == 0 <=> inside the valid grid and no agent there (:43-51)
+                bool free_cell = (unsigned)(tr - O) < (unsigned)R && (unsigned)(tc - O) <= (unsigned)C;
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+                    if (k != i) free_cell = free_cell && !(ar[k] == tr && ac[k] == tc);
+                const bool moved = wants && free_cell;
+                const bool penal = (ai != 0) && !moved;  // :184-186, any other action included
+                if (moved) { ar[i] = tr; ac[i] = tc; }
+                double col = 0.0;  // get_reward, :190-225
+                const int ii = ar[i] - O, jj = ac[i] - O;
+                if (jj < C) {
+                    const int bit = ii * C + jj;
+                    if ((rem >> bit) & 1ull) {
+                        rem &= ~(1ull << bit);
+                        const int color = (ii + jj) & 1;
+                        if (color == 0) ng[i] += 1; else no[i] += 1;
+                        col = (color == (int)((goals >> i) & 1u)) ? 1.0 : -0.5;
+                    }
+                }
+                rew[i] = (penal ? -0.1 : 0.0) + col;  // penalty + get_reward, :236
+                total += rew[i];                      // np.sum, :243
+            }
+            steps = (steps + 1) & 0xFFFFFF;  // :244
+            bool done;                       // :246-260
+            if (N == 1) {
+                const uint64_t mine = (goals & 1) ? Gm::color_all(1) : Gm::color_all(0);
+                done = (steps == p.max_steps) || ((rem & mine) == 0ull);
+            } else {
+                done = (steps == p.max_steps) || (rem == 0ull);
+            }
+            if (valid) {
+                if (p.local_rewards != nullptr) {
+                    double mine = rew[0];
+#pragma unroll
+                    for (int i = 1; i < N; ++i) mine = (a == i) ? rew[i] : mine;
+                    reinterpret_cast<Real *>(p.local_rewards)[((size_t)t * B + env) * N + a] = (Real)mine;
+                }
+                if (a == 0) {
+                    if (p.reward != nullptr) reinterpret_cast<Real *>(p.reward)[(size_t)t * B + env] = (Real)total;
+                    if (p.done != nullptr) p.done[(size_t)t * B + env] = done ? 1 : 0;
+                }
+            }
+            if (p.auto_reset && done) reset_state();
+        }
+        emit(t);
+        if (sel && a == 0 && p.done != nullptr) p.done[env] = 0;  // checkers.py:291
+    }
+
+    // ---- store compact state
+    if (valid && a == 0) {
+        p.remaining[env] = rem;
+        p.meta[env] = (uint32_t)steps | (goals << 24);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            p.agents[(size_t)env * N + i] =
+                (uint32_t)ar[i] | ((uint32_t)ac[i] << 8) | ((uint32_t)ng[i] << 16) | ((uint32_t)no[i] << 24);
+    }
+    if (pending && lane < 2) bulk_wait_all();  // smem must outlive the async reads
+}
+
+// ------------------------------------------------------------------------ host side
+
+template <int R, int C, int O, int N, typename Real>
+static int launch_ck(const CkParams &p, cudaStream_t stream) {
+    using Gm = CkGeom<R, C, O, N, Real>;
+    auto kern = checkers_kernel<R, C, O, N, Real>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    CM3_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::kSmemBytes));
+        attr_set[dev] = true;
+    }
+    const int ntiles = (p.B + Gm::EW - 1) / Gm::EW;
+    const int nblocks = (ntiles + kCkWarpsPerBlock - 1) / kCkWarpsPerBlock;
+    kern<<<nblocks, kCkWarpsPerBlock * kWarp, Gm::kSmemBytes, stream>>>(p);
+    CM3_CUDA(cudaGetLastError());
+    return CM3_OK;
+}
+
+#define CM3_CK_GEOMS(X) \
+    X(3, 8, 2)          \
+    X(3, 16, 2)         \
+    X(3, 2, 2)          \
+    X(3, 4, 2)          \
+    X(5, 8, 2)          \
+    X(3, 8, 1)          \
+    X(3, 8, 3)
+
+template <typename Real>
+static int dispatch_ck(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
+#define X(r, c, o)                                                      \
+    if (R == r && C == c && O == o) {                                   \
+        switch (N) {                                                    \
+            case 1: return launch_ck<r, c, o, 1, Real>(p, stream);      \
+            case 2: return launch_ck<r, c, o, 2, Real>(p, stream);      \
+            case 3: return launch_ck<r, c, o, 3, Real>(p, stream);      \
+            case 4: return launch_ck<r, c, o, 4, Real>(p, stream);      \
+            default: break;                                             \
+        }                                                               \
+    }
+    CM3_CK_GEOMS(X)
+#undef X
+    set_error("no compiled Checkers kernel for n_rows=%d n_columns=%d n_obs=%d n_agents=%d", R, C, O, N);
+    return CM3_ERR_UNSUPPORTED;
+}
+
+bool checkers_geometry_supported(int R, int C, int O, int N) {
+    if (N < 1 || N > CM3_MAX_AGENTS) return false;
+#define X(r, c, o) \
+    if (R == r && C == c && O == o) return true;
+    CM3_CK_GEOMS(X)
+#undef X
+    return false;
+}
+
+int checkers_launch(int R, int C, int O, int N, int real, const CkParams &p, cudaStream_t stream) {
+    if (real == CM3_REAL_F64) return dispatch_ck<double>(R, C, O, N, p, stream);
+    return dispatch_ck<float>(R, C, O, N, p, stream);
+}
+
+}  // namespace cm3

@@ -1,0 +1,220 @@
+"""VecParticle - B instances of MultiAgentEnv + the multi-goal_spread scenario
+(multiagent/environment.py, core.py, scenarios/multi-goal_spread.py) stepped by one CUDA kernel
+launch.  torch tensors only hold the buffers; the computation is in libcm3env.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+FIELDS = L.ParticleOutputs.FIELDS
+OBS_FIELDS = ("global_state", "obs_others", "obs_self")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VecParticle(object):
+    """`config` is the dict of a config_particle_*.json (agents_x/y, landmarks_x/y, initial_std),
+    `prob_random` the make_world argument (multi-goal_spread.py:19), `max_steps` the
+    MultiAgentEnv argument (environment.py:16).  dtype float64 = free-running parity mode."""
+
+    def __init__(self, num_envs, n_agents, config, prob_random=0.0, max_steps=50,
+                 device="cuda:0", dtype=torch.float32, env_id_offset=0, **world_overrides):
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self.lib = L.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.Cm3Error(-5, "VecParticle needs a CUDA device (got %r); there is no CPU path" % (device,))
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.B, self.N = int(num_envs), int(n_agents)
+        if self.N > L.MAX_AGENTS:
+            raise L.Cm3Error(-4, "n_agents=%d: at most %d agents are supported" % (self.N, L.MAX_AGENTS))
+        self.max_steps = int(max_steps)
+        self.dtype = dtype
+        self.L_others = 4 * max(self.N - 1, 1)
+        self.config = dict(config)
+        self.prob_random = float(prob_random)
+
+        cfg = L.ParticleConfig()
+        self.lib.cm3_particle_default_config(C.byref(cfg), self.N, self.max_steps)
+        cfg.num_envs = self.B
+        cfg.real = L.REAL_F64 if dtype == torch.float64 else L.REAL_F32
+        cfg.device = dev_index
+        cfg.env_id_offset = int(env_id_offset)
+        for i in range(self.N):
+            cfg.agents_x[i] = float(config["agents_x"][i])
+            cfg.agents_y[i] = float(config["agents_y"][i])
+            cfg.landmarks_x[i] = float(config["landmarks_x"][i])
+            cfg.landmarks_y[i] = float(config["landmarks_y"][i])
+        cfg.initial_std = float(config.get("initial_std", 0.0))
+        cfg.prob_random = self.prob_random
+        for k, v in world_overrides.items():  # dt, damping, contact_force, contact_margin, ...
+            if not hasattr(cfg, k):
+                raise TypeError("unknown world constant %r" % k)
+            setattr(cfg, k, float(v))
+        self.cfg = cfg
+        h = C.c_void_p()
+        L.check(self.lib.cm3_particle_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+        dev = self.device
+        B, N = self.B, self.N
+        self.state = dict(
+            sv=torch.zeros(B, N, 4, dtype=dtype, device=dev),
+            landmarks=torch.zeros(B, N, 2, dtype=dtype, device=dev),
+            steps=torch.zeros(B, dtype=torch.int32, device=dev),
+            collisions=torch.zeros(B, dtype=torch.int32, device=dev),
+            reached=torch.zeros(B, dtype=torch.uint8, device=dev))
+        self._st = L.ParticleState(*[_ptr(self.state[k]) for k in
+                                     ("sv", "landmarks", "steps", "collisions", "reached")])
+        self.out = self.alloc_outputs()
+        self._out_c = self._outputs_struct(self.out)
+        self._actions_dev = torch.zeros(B, N, dtype=torch.int8, device=dev)
+        self._host = None
+        self._reset_counter = 0
+
+    # ------------------------------------------------------------------ buffers
+    def field_shapes(self):
+        B, N = self.B, self.N
+        return dict(global_state=(B, N, 4), obs_others=(B, N, self.L_others), obs_self=(B, N, 4),
+                    reward=(B,), reward_n=(B, N), done=(B,))
+
+    def bytes_per_env_step(self):
+        """Algorithmic bytes of one env-step."""
+        el = 8 if self.dtype == torch.float64 else 4
+        N = self.N
+        out = sum(int(np.prod(s[1:])) for k, s in self.field_shapes().items() if k != "done") * el + 1
+        state = 2 * (4 * N * el) + 2 * N * el + 2 * 4 + 2 * 4 + 2  # sv rw, landmarks r, steps rw, collisions rw, reached rw
+        return out + state + N
+
+    def alloc_outputs(self, T=None, pinned_host=False):
+        lead = () if T is None else (int(T),)
+        out = {}
+        for k, shp in self.field_shapes().items():
+            dt = torch.uint8 if k == "done" else self.dtype
+            if pinned_host:
+                out[k] = torch.zeros(lead + shp, dtype=dt).pin_memory()
+            else:
+                out[k] = torch.zeros(lead + shp, dtype=dt, device=self.device)
+        return out
+
+    @staticmethod
+    def _outputs_struct(out):
+        return L.ParticleOutputs(*[_ptr(out.get(f)) for f in FIELDS])
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.cm3_particle_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ API
+    def reset(self, init_pos=None, init_landmarks=None, mask=None, seed=0, reset_counter=None):
+        """MultiAgentEnv.reset().  With init_pos / init_landmarks ([B,N,2]) the state that
+        reset_world() drew on the host is injected (parity protocol); otherwise the device draws
+        it from Philox keyed by (seed, global env id, reset_counter)."""
+        ip = il = None
+        if init_pos is not None:
+            if init_landmarks is None:
+                raise ValueError("init_pos and init_landmarks must be given together")
+            ip = torch.as_tensor(np.asarray(init_pos)).to(device=self.device, dtype=self.dtype).reshape(self.B, self.N, 2).contiguous()
+            il = torch.as_tensor(np.asarray(init_landmarks)).to(device=self.device, dtype=self.dtype).reshape(self.B, self.N, 2).contiguous()
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+            if m.shape != (self.B,):
+                raise ValueError("mask must have shape [num_envs]")
+        if reset_counter is None:
+            reset_counter = self._reset_counter
+            self._reset_counter += 1
+        L.check(self.lib.cm3_particle_reset(self._h, C.byref(self._st), _ptr(ip), _ptr(il), _ptr(m),
+                                            int(seed) & (2**64 - 1), int(reset_counter),
+                                            C.byref(self._out_c), self._stream()))
+        self._keep = (ip, il, m)
+        return self.out
+
+    def _actions_tensor(self, actions, lead=()):
+        shape = tuple(lead) + (self.B, self.N)
+        if torch.is_tensor(actions):
+            a = actions
+            if a.dtype != torch.int8:
+                a = a.clamp(-128, 127).to(torch.int8)
+            a = a.to(self.device).reshape(shape).contiguous()
+        else:
+            a = np.clip(np.asarray(actions, dtype=np.int64), -128, 127).astype(np.int8).reshape(shape)
+            a = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        return a
+
+    def step(self, actions):
+        """MultiAgentEnv.step(action_n) for all envs; actions [B,N] ints (values outside 1..4
+        apply no force, environment.py:197-200)."""
+        a = self._actions_tensor(actions)
+        L.check(self.lib.cm3_particle_step(self._h, C.byref(self._st), _ptr(a),
+                                           C.byref(self._out_c), self._stream()))
+        self._keep = a
+        return self.out
+
+    def rollout(self, T, actions=None, seed=0, t0=0, auto_reset=False, out=None,
+                record_actions=False):
+        T = int(T)
+        if out is None:
+            out = self.alloc_outputs(T)
+        a = None if actions is None else self._actions_tensor(actions, (T,))
+        rec = torch.zeros(T, self.B, self.N, dtype=torch.int8, device=self.device) if record_actions else None
+        oc = self._outputs_struct(out)
+        L.check(self.lib.cm3_particle_rollout(self._h, C.byref(self._st), _ptr(a), int(seed) & (2**64 - 1),
+                                              int(t0), T, 1 if auto_reset else 0, _ptr(rec),
+                                              C.byref(oc), self._stream()))
+        self._keep = (a, oc)
+        if record_actions:
+            out = dict(out)
+            out["actions"] = rec
+        return out
+
+    def step_host(self, actions, fields=FIELDS):
+        if self._host is None:
+            self._host = self.alloc_outputs(pinned_host=True)
+            self._host_actions = torch.zeros(self.B, self.N, dtype=torch.int8).pin_memory()
+        self._host_actions.numpy()[...] = np.clip(np.asarray(actions), -128, 127).astype(np.int8).reshape(self.B, self.N)
+        oh = L.ParticleOutputs(*[_ptr(self._host[f]) if f in fields else None for f in FIELDS])
+        L.check(self.lib.cm3_particle_step_host(self._h, C.byref(self._st), _ptr(self._host_actions),
+                                                _ptr(self._actions_dev), C.byref(self._out_c),
+                                                C.byref(oh), self._stream()))
+        return {f: self._host[f].numpy() for f in fields}
+
+    # ------------------------------------------------------------------ state
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.state.items()}
+
+    def load_state_dict(self, sd):
+        for k in self.state:
+            self.state[k].copy_(torch.as_tensor(sd[k]).to(self.state[k].dtype))
+
+    def set_state(self, pos=None, vel=None, landmarks=None, steps=None, collisions=None, reached=None):
+        """State injection (parity protocol)."""
+        def t(x, dt):
+            return torch.as_tensor(np.asarray(x)).to(device=self.device, dtype=dt)
+        if vel is not None:
+            self.state["sv"][:, :, 0:2] = t(vel, self.dtype).reshape(self.B, self.N, 2)
+        if pos is not None:
+            self.state["sv"][:, :, 2:4] = t(pos, self.dtype).reshape(self.B, self.N, 2)
+        if landmarks is not None:
+            self.state["landmarks"].copy_(t(landmarks, self.dtype).reshape(self.B, self.N, 2))
+        if steps is not None:
+            self.state["steps"].copy_(t(steps, torch.int32))
+        if collisions is not None:
+            self.state["collisions"].copy_(t(collisions, torch.int32))
+        if reached is not None:
+            r = np.asarray(reached)
+            if r.ndim == 2:  # [B,N] flags -> bitmask
+                r = (r.astype(np.uint8) << np.arange(self.N, dtype=np.uint8)).sum(axis=1)
+            self.state["reached"].copy_(t(r, torch.uint8))

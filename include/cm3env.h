@@ -1,0 +1,223 @@
+/*
+ * cm3env.h - C ABI of the B200 batched environment stepper (libcm3env.so).
+ *
+ * The reference (011235813/cm3) has no FFI: its "plugin API" for this path is two Python
+ * object protocols, Checkers.reset/step (env/checkers.py:265,228) and
+ * MultiAgentEnv.reset/step + the scenario callbacks (multiagent/environment.py:125,81;
+ * multiagent/scenarios/multi-goal_spread.py:19-154).  The Python facades in cm3_b200/
+ * keep those protocols; everything they compute goes through the entry points below,
+ * which are what a ctypes / cgo / JNI binding on the reference side would bind
+ * (INTEGRATION.md shows the ctypes stub).
+ *
+ * Conventions
+ *  - plain C types only; every function returns a cm3_status (0 = ok, < 0 = error) and
+ *    leaves a message retrievable with cm3_last_error() (thread local);
+ *  - the library owns no HBM: state, action and output buffers are allocated by the
+ *    caller (the facades hold them in torch tensors) and passed as raw device pointers;
+ *    they must outlive the stream work.  A handle holds only configuration;
+ *  - all device work is enqueued on the caller's stream (cudaStream_t passed as void*,
+ *    NULL = legacy default stream); nothing synchronises except the *_host entry points;
+ *  - there is NO CPU implementation behind this ABI: without a CUDA device every compute
+ *    entry point fails with CM3_ERR_NO_DEVICE;
+ *  - a handle is used by one host thread at a time; handles are independent.
+ *
+ * Batched layout ("B" = num_envs on this device, "N" = n_agents, Real = float or double
+ * as selected by cfg.real):
+ *  every output field is its own dense array [B][...] (or [T][B][...] for rollouts), so a
+ *  learner can consume a field directly as a batch tensor.
+ */
+#ifndef CM3ENV_H
+#define CM3ENV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM3_ABI_VERSION 1
+#define CM3_MAX_AGENTS 4
+
+typedef enum {
+    CM3_OK = 0,
+    CM3_ERR_BAD_ARG = -1,     /* NULL handle / pointer, bad enum, bad mask */
+    CM3_ERR_BAD_SHAPE = -2,   /* geometry the reference itself rejects (checkers.py:16-17) */
+    CM3_ERR_CUDA = -3,        /* a CUDA runtime call failed; message has the CUDA error */
+    CM3_ERR_UNSUPPORTED = -4, /* geometry / agent count without a compiled kernel */
+    CM3_ERR_NO_DEVICE = -5    /* no CUDA device: there is no CPU fallback */
+} cm3_status;
+
+typedef enum { CM3_REAL_F32 = 0, CM3_REAL_F64 = 1 } cm3_real;
+
+int cm3_abi_version(void);
+const char *cm3_last_error(void);
+/* number of visible CUDA devices (0 when the driver is absent) */
+int cm3_device_count(int *count);
+
+/* ------------------------------------------------------------------ Checkers */
+
+/* Mirrors Checkers.__init__(n_rows, n_columns, n_obs, agents_r, agents_c, n_agents,
+ * max_steps) - env/checkers.py:5-35.  agents_r / agents_c are BEFORE the n_obs expansion,
+ * exactly as the reference takes them. */
+typedef struct {
+    int32_t n_rows, n_columns, n_obs, n_agents, max_steps;
+    int32_t agents_r[CM3_MAX_AGENTS];
+    int32_t agents_c[CM3_MAX_AGENTS];
+    int32_t num_envs;      /* B on this device */
+    int32_t real;          /* cm3_real of the float outputs */
+    int32_t device;        /* CUDA ordinal */
+    int32_t reserved;
+    int64_t env_id_offset; /* global id of local env 0 (keys the Philox streams, so results
+                              do not depend on how the batch is sharded over GPUs) */
+} cm3_checkers_config;
+
+/* Compact per-env state (device pointers, caller-owned):
+ *   remaining[b]  bit i*n_columns+j set <=> valid-grid cell (i,j) still holds its reward
+ *                 (the green/orange colour is a function of (i+j) parity, checkers.py:54-63)
+ *   agents[b][n]  r | c<<8 | n_green<<16 | n_orange<<24, (r,c) in expanded coordinates
+ *   meta[b]       steps (bits 0-23) | goal index of agent n at bit 24+n */
+typedef struct {
+    uint64_t *remaining; /* [B]    */
+    uint32_t *agents;    /* [B][N] */
+    uint32_t *meta;      /* [B]    */
+} cm3_checkers_state;
+
+/* Outputs of reset/step (env/checkers.py:262,291), dense per field.  For rollouts every
+ * pointer addresses [T][B][...].  Any pointer may be NULL: that field is not written. */
+typedef struct {
+    void *grid;          /* [B][n_rows][n_columns+1][2]   Real  get_valid_grid  :66-76  */
+    void *vec;           /* [B][N][4]                      Real  get_global_state :89-93 */
+    void *obs_others;    /* [B][N][2*max(N-1,1)]           Real  :143-151 */
+    void *obs_self_t;    /* [B][N][2*n_obs+1][2*n_obs+1][3] Real get_obs :97-109 */
+    void *obs_self_v;    /* [B][N][4]                      Real  :137-139 */
+    void *reward;        /* [B]                            Real  np.sum(local_rewards) :243 */
+    void *local_rewards; /* [B][N]                         Real  :232-237 */
+    uint8_t *done;       /* [B]                                  :246-260 */
+} cm3_checkers_outputs;
+
+typedef struct cm3_checkers_s *cm3_checkers_t;
+
+int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out);
+int cm3_checkers_destroy(cm3_checkers_t h);
+
+/* Checkers.reset(goals) for the envs selected by env_mask (NULL = all).  goal_idx is
+ * [B][N] uint8 on the device, goal_idx[b][n] = argmax(goals[n]) in {0,1} (checkers.py:235);
+ * NULL = agent n gets goal n & 1 (np.eye(n_agents) for N = 2, train_offpolicy.py:298).
+ * Observations of ALL envs are written to outs (fresh for reset envs, current otherwise);
+ * reward / local_rewards are not touched, done is written as 0 for the reset envs. */
+int cm3_checkers_reset(cm3_checkers_t h, const cm3_checkers_state *st, const uint8_t *goal_idx,
+                       const uint8_t *env_mask, const cm3_checkers_outputs *outs, void *stream);
+
+/* Checkers.step(actions): actions [B][N] int8 on the device.  Values outside 0..4 are
+ * legal and earn the -0.1 penalty (checkers.py:184-186). */
+int cm3_checkers_step(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                      const cm3_checkers_outputs *outs, void *stream);
+
+/* T fused steps in one launch; state stays in registers between steps.
+ *   actions      [T][B][N] int8 device, or NULL: uniform actions in {0..4} are drawn on the
+ *                device from Philox4x32-10 keyed by (seed; global env id, t0 + t)
+ *   actions_out  [T][B][N] int8 device or NULL: the actions that were applied
+ *   auto_reset   0: reference behaviour (keeps stepping past done)
+ *                1: an env whose step returned done is reset inside the kernel (same goals)
+ *                   and the observations written for that step are those of the fresh
+ *                   episode; reward / done still describe the terminal transition
+ *   outs         [T][B][...] per field */
+int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                         uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
+                         int8_t *actions_out, const cm3_checkers_outputs *outs, void *stream);
+
+/* Host-buffer form of step: copies actions_host -> actions_dev, steps, copies every
+ * non-NULL field of outs_host back from the matching field of outs_dev and waits for the
+ * stream.  This is the call a host-side binding uses when its buffers live in host memory
+ * (pinned memory makes the copies asynchronous with respect to other streams). */
+int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st,
+                           const int8_t *actions_host, int8_t *actions_dev,
+                           const cm3_checkers_outputs *outs_dev,
+                           const cm3_checkers_outputs *outs_host, void *stream);
+
+/* ------------------------------------------------------------------ Particle */
+
+/* World / scenario constants (defaults = the reference's, filled by
+ * cm3_particle_default_config) and the multi-goal_spread presets. */
+typedef struct {
+    int32_t n_agents;  /* agents == landmarks, multi-goal_spread.py:36-37 */
+    int32_t max_steps; /* MultiAgentEnv(max_steps=...), environment.py:16 */
+    int32_t num_envs;
+    int32_t real;      /* cm3_real of state AND outputs (F64 = free-running parity mode) */
+    int32_t device;
+    int32_t reserved;
+    int64_t env_id_offset;
+    double dt;             /* core.py:94   */
+    double damping;        /* core.py:96   */
+    double contact_force;  /* core.py:98   */
+    double contact_margin; /* core.py:99   */
+    double agent_size;     /* multi-goal_spread.py:47 */
+    double mass;           /* core.py:47-51 */
+    double sensitivity;    /* environment.py:211 */
+    double reach_thresh;   /* multi-goal_spread.py:126 */
+    /* reset presets, multi-goal_spread.py:29-35 and alg/config_particle_*.json */
+    double agents_x[CM3_MAX_AGENTS], agents_y[CM3_MAX_AGENTS];
+    double landmarks_x[CM3_MAX_AGENTS], landmarks_y[CM3_MAX_AGENTS];
+    double initial_std;
+    double prob_random;
+} cm3_particle_config;
+
+void cm3_particle_default_config(cm3_particle_config *cfg, int32_t n_agents, int32_t max_steps);
+
+/* State (device, caller-owned).  sv rows are (vel.x, vel.y, pos.x, pos.y) - the same
+ * layout as the reference's global_state rows (environment.py:113-116). */
+typedef struct {
+    void *sv;            /* [B][N][4] Real */
+    void *landmarks;     /* [B][N][2] Real  landmark.state.p_pos */
+    int32_t *steps;      /* [B]  env.steps */
+    int32_t *collisions; /* [B]  scenario.collisions (episode total, double counted :135-137) */
+    uint8_t *reached;    /* [B]  bit n = agents[n].reached */
+} cm3_particle_state;
+
+typedef struct {
+    void *global_state; /* [B][N][4]              Real environment.py:113-116 */
+    void *obs_others;   /* [B][N][4*max(N-1,1)]   Real multi-goal_spread.py:146-154 */
+    void *obs_self;     /* [B][N][4]              Real */
+    void *reward;       /* [B]                    Real np.sum(reward_n), environment.py:107 */
+    void *reward_n;     /* [B][N]                 Real multi-goal_spread.py:121-138 */
+    uint8_t *done;      /* [B]                         environment.py:118-121 */
+} cm3_particle_outputs;
+
+typedef struct cm3_particle_s *cm3_particle_t;
+
+int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out);
+int cm3_particle_destroy(cm3_particle_t h);
+
+/* MultiAgentEnv.reset() for the envs selected by env_mask (NULL = all).
+ *   init_pos / init_landmarks  [B][N][2] Real device: the state reset_world() produced on the
+ *       host (parity protocol: inject the reference's draws).  If NULL the device draws them:
+ *       multi-goal_spread.py:75-91 re-expressed on Philox4x32-10 keyed by
+ *       (seed; global env id, reset_counter) - u < prob_random -> uniform(-1,1) agents and
+ *       landmarks, else presets + N(0, initial_std) on the agents.
+ * Velocities, steps, collisions and reached are zeroed; observations of all envs are written
+ * to outs (reward fields untouched, done = 0 for the reset envs). */
+int cm3_particle_reset(cm3_particle_t h, const cm3_particle_state *st, const void *init_pos,
+                       const void *init_landmarks, const uint8_t *env_mask, uint64_t seed,
+                       int64_t reset_counter, const cm3_particle_outputs *outs, void *stream);
+
+/* MultiAgentEnv.step(action_n): actions [B][N] int8 device; values outside 1..4 apply no
+ * force (environment.py:197-200). */
+int cm3_particle_step(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                      const cm3_particle_outputs *outs, void *stream);
+
+/* T fused steps; same contract as cm3_checkers_rollout.  With auto_reset the fresh episode is
+ * drawn as in cm3_particle_reset with reset_counter = t0 + t + 1. */
+int cm3_particle_rollout(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                         uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
+                         int8_t *actions_out, const cm3_particle_outputs *outs, void *stream);
+
+int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st,
+                           const int8_t *actions_host, int8_t *actions_dev,
+                           const cm3_particle_outputs *outs_dev,
+                           const cm3_particle_outputs *outs_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CM3ENV_H */

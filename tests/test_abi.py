@@ -1,0 +1,86 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/cm3env.h declares, and
+refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import cm3_b200
+from cm3_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "cm3env.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cm3_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    cm3_b200.build_library()
+    lib = L.load_library()
+    assert lib.cm3_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    cm3_b200.build_library()
+    lib = C.CDLL(cm3_b200.library_path())
+    names = header_functions()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), "library does not export %s" % name
+        assert name in L.SYMBOLS, "ctypes binding does not cover %s" % name
+    assert sorted(L.SYMBOLS) == names
+
+
+def test_struct_sizes_match_header():
+    # natural alignment, no packing: sizes derived by hand from include/cm3env.h
+    assert C.sizeof(L.CheckersConfig) == 5 * 4 + 2 * 16 + 4 * 4 + 4 + 8  # padded to 8
+    assert C.sizeof(L.CheckersState) == 24
+    assert C.sizeof(L.CheckersOutputs) == 64
+    assert C.sizeof(L.ParticleConfig) == 6 * 4 + 8 + 8 * 8 + 4 * 32 + 16
+    assert C.sizeof(L.ParticleState) == 40
+    assert C.sizeof(L.ParticleOutputs) == 48
+
+
+def test_bad_geometry_is_rejected_like_the_reference():
+    lib = L.load_library()
+    cfg = L.CheckersConfig(n_rows=4, n_columns=8, n_obs=2, n_agents=2, max_steps=33, num_envs=4)
+    h = C.c_void_p()
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -2  # checkers.py:16
+    cfg = L.CheckersConfig(n_rows=3, n_columns=7, n_obs=2, n_agents=2, max_steps=33, num_envs=4)
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -2  # checkers.py:17
+    assert b"odd" in lib.cm3_last_error()
+    cfg = L.CheckersConfig(n_rows=7, n_columns=30, n_obs=2, n_agents=2, max_steps=33, num_envs=4)
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -4  # no compiled kernel
+
+
+def test_null_arguments():
+    lib = L.load_library()
+    assert lib.cm3_checkers_create(None, None) == -1
+    assert lib.cm3_checkers_destroy(None) == -1
+    assert lib.cm3_particle_destroy(None) == -1
+    assert lib.cm3_checkers_step(None, None, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = L.load_library()
+    assert L.device_count() == 0
+    cfg = L.CheckersConfig(n_rows=3, n_columns=8, n_obs=2, n_agents=2, max_steps=33, num_envs=4)
+    cfg.agents_r[0], cfg.agents_r[1], cfg.agents_c[0], cfg.agents_c[1] = 0, 2, 8, 8
+    h = C.c_void_p()
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -5
+    assert b"no CPU fallback" in lib.cm3_last_error()
+    pc = L.ParticleConfig()
+    lib.cm3_particle_default_config(C.byref(pc), 4, 33)
+    assert (pc.dt, pc.damping, pc.contact_force, pc.contact_margin) == (0.1, 0.25, 100.0, 1e-3)
+    assert lib.cm3_particle_create(C.byref(pc), C.byref(h)) == -5
+    with pytest.raises(L.Cm3Error):
+        cm3_b200.VecCheckers(4, device="cpu")
+    with pytest.raises(L.Cm3Error):
+        cm3_b200.VecCheckers(4, 3, 8, 2, [0, 2], [8, 8], 2, 33, device="cuda:0")

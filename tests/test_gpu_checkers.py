@@ -1,0 +1,232 @@
+"""GPU parity tests for the Checkers kernels, through the C ABI (VecCheckers -> ctypes ->
+libcm3env.so).  Bar: bit-exact against the reference goldens / the oracle (float32 outputs equal
+float32(reference float64); float64 outputs equal the reference's float64)."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import oracle
+from cm3_b200 import VecCheckers, presets
+
+pytestmark = pytest.mark.gpu
+
+CK2 = dict(presets.CHECKERS["stage2"], max_steps=presets.MAX_STEPS)
+CK1 = dict(presets.CHECKERS["stage1"], max_steps=presets.MAX_STEPS)
+
+
+def cmp_fields(out, ref, fields, cast, msg):
+    for f in fields:
+        got = out[f].cpu().numpy() if torch.is_tensor(out[f]) else out[f]
+        want = ref[f]
+        if f != "done":
+            want = want.astype(cast)
+        np.testing.assert_array_equal(got, want, err_msg="%s %s" % (msg, f))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name", gu.fixtures("checkers"))
+def test_golden_replay(name, dtype):
+    fix = gu.load(name)
+    ctor = gu.checkers_ctor(fix)
+    K = fix["actions"].shape[0]
+    env = VecCheckers(K, dtype=dtype, **ctor)
+    cast = np.float32 if dtype == torch.float32 else np.float64
+    for s, op in enumerate(fix["ops"]):
+        ref = {f: fix[f][:, s] for f in gu.CHECKERS_FIELDS}
+        if op == gu.RESET:
+            out = env.reset(goals=fix["goals"][:, s])
+            cmp_fields(out, ref, ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "done"),
+                       cast, "%s op %d reset" % (name, s))
+        else:
+            out = env.step(fix["actions"][:, s])
+            cmp_fields(out, ref, gu.CHECKERS_FIELDS, cast, "%s op %d step" % (name, s))
+
+
+def run_oracle_vs_cuda(B, ctor, T, seed, goal_idx=None, dtype=torch.float32):
+    rng = np.random.default_rng(seed)
+    N = ctor["n_agents"]
+    actions = rng.integers(0, 5, size=(T, B, N)).astype(np.int8)
+    actions[rng.random(actions.shape) < 0.02] = 7
+    if goal_idx is None:
+        goal_idx = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
+    orc = oracle.OracleCheckers(B, nthreads=oracle.max_threads(), **ctor)
+    env = VecCheckers(B, dtype=dtype, **ctor)
+    cast = np.float32 if dtype == torch.float32 else np.float64
+    ref = orc.reset(goal_idx)
+    out = env.reset(goal_idx=goal_idx)
+    cmp_fields(out, ref, ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "done"), cast, "reset")
+    for t in range(T):
+        ref = orc.step(actions[t])
+        out = env.step(actions[t])
+        cmp_fields(out, ref, gu.CHECKERS_FIELDS, cast, "t=%d" % t)
+    return env, orc, actions, goal_idx
+
+
+@pytest.mark.parametrize("B", [1, 15, 16, 17, 250, 4096])
+def test_oracle_parity_ck2_ragged_batches(B):
+    """Tile tails: B not a multiple of the 16 envs a warp owns takes the non-TMA flush path."""
+    run_oracle_vs_cuda(B, CK2, 45, seed=B)
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 1000])
+def test_oracle_parity_ck1(B):
+    run_oracle_vs_cuda(B, CK1, 45, seed=100 + B)
+
+
+@pytest.mark.parametrize("N", [3, 4])
+def test_oracle_parity_more_agents(N):
+    ctor = dict(n_rows=3, n_columns=8, n_obs=2, agents_r=[0, 2, 1, 1][:N], agents_c=[8, 8, 8, 7][:N],
+                n_agents=N, max_steps=40)
+    run_oracle_vs_cuda(77, ctor, 60, seed=N)
+
+
+@pytest.mark.parametrize("geom", [(3, 16, 2), (5, 8, 2), (3, 8, 1), (3, 8, 3), (3, 4, 2)])
+def test_oracle_parity_other_geometries(geom):
+    R, Cc, O = geom
+    ctor = dict(n_rows=R, n_columns=Cc, n_obs=O, agents_r=[0, R - 1], agents_c=[Cc, Cc], n_agents=2,
+                max_steps=50)
+    run_oracle_vs_cuda(130, ctor, 70, seed=R * 100 + Cc)
+
+
+def test_rollout_equals_stepping_and_is_bit_exact():
+    """One fused T-step launch == T single-step launches == oracle (headline config, B=8192)."""
+    B, T = 8192, presets.MAX_STEPS + 7
+    rng = np.random.default_rng(7)
+    actions = rng.integers(0, 5, size=(T, B, 2)).astype(np.int8)
+    orc = oracle.OracleCheckers(B, nthreads=oracle.max_threads(), **CK2)
+    env = VecCheckers(B, **CK2)
+    orc.reset(np.array([[0, 1]]))
+    env.reset(goals=np.eye(2))
+    ro = env.rollout(T, actions=actions)
+    for t in range(T):
+        ref = orc.step(actions[t])
+        cmp_fields({f: ro[f][t] for f in gu.CHECKERS_FIELDS}, ref, gu.CHECKERS_FIELDS, np.float32, "t=%d" % t)
+    st = env.unpack_state()
+    np.testing.assert_array_equal(st["steps"], orc.steps())
+
+
+def test_philox_actions_match_cpu_twin_and_shard_invariance():
+    B, T = 1024, 12
+    env = VecCheckers(B, **CK2)
+    env.reset(goals=np.eye(2))
+    ro = env.rollout(T, actions=None, seed=presets.SEED, t0=5, record_actions=True)
+    want = oracle.philox_actions(presets.SEED, 0, B, 2, 5, T)
+    np.testing.assert_array_equal(ro["actions"].cpu().numpy(), want)
+    # the same envs as a shard with env_id_offset see the same stream -> identical results
+    half = VecCheckers(B // 2, env_id_offset=B // 2, **CK2)
+    half.reset(goals=np.eye(2))
+    rh = half.rollout(T, actions=None, seed=presets.SEED, t0=5)
+    for f in gu.CHECKERS_FIELDS:
+        assert torch.equal(rh[f], ro[f][:, B // 2:]), f
+
+
+def test_auto_reset_properties():
+    """auto_reset: after a done step the env restarts (observations of the fresh episode are
+    returned); the episode that follows is identical to a manual reset + replay."""
+    B, T = 512, 3 * presets.MAX_STEPS
+    rng = np.random.default_rng(3)
+    actions = rng.integers(0, 5, size=(T, B, 2)).astype(np.int8)
+    env = VecCheckers(B, **CK2)
+    first = {k: v.clone() for k, v in env.reset(goals=np.eye(2)).items()}
+    ro = env.rollout(T, actions=actions, auto_reset=True)
+    done = ro["done"].cpu().numpy()
+    # random walks never clear the 3x8 board in 33 steps -> done exactly every max_steps
+    want_done = np.zeros((T, B), dtype=np.uint8)
+    want_done[presets.MAX_STEPS - 1::presets.MAX_STEPS] = 1
+    np.testing.assert_array_equal(done, want_done)
+    for t in np.nonzero(want_done[:, 0])[0]:
+        for f in ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v"):
+            assert torch.equal(ro[f][t], first[f]), (t, f)
+    # second episode == fresh env fed the second episode's actions
+    env2 = VecCheckers(B, **CK2)
+    env2.reset(goals=np.eye(2))
+    ro2 = env2.rollout(presets.MAX_STEPS - 1, actions=actions[presets.MAX_STEPS:2 * presets.MAX_STEPS - 1])
+    for f in gu.CHECKERS_FIELDS:
+        assert torch.equal(ro2[f], ro[f][presets.MAX_STEPS:2 * presets.MAX_STEPS - 1]), f
+
+
+def test_masked_reset_and_state_roundtrip():
+    B = 100
+    rng = np.random.default_rng(11)
+    env = VecCheckers(B, **CK2)
+    orc = oracle.OracleCheckers(B, **CK2)
+    g = np.tile(np.array([[0, 1]], dtype=np.uint8), (B, 1))
+    env.reset(goal_idx=g)
+    orc.reset(g)
+    for t in range(10):
+        a = rng.integers(0, 5, size=(B, 2))
+        env.step(a)
+        orc.step(a)
+    mask = (rng.random(B) < 0.4).astype(np.uint8)
+    g2 = rng.integers(0, 2, size=(B, 2)).astype(np.uint8)
+    out = env.reset(goal_idx=g2, mask=mask)
+    ref = orc.reset(g2, mask=mask)
+    cmp_fields(out, ref, ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v"), np.float32, "masked reset")
+    sd = env.state_dict()
+    a = rng.integers(0, 5, size=(B, 2))
+    o1 = {k: v.clone() for k, v in env.step(a).items()}
+    cmp_fields(o1, orc.step(a), gu.CHECKERS_FIELDS, np.float32, "after masked reset")
+    env.load_state_dict(sd)
+    o2 = env.step(a)
+    for f in gu.CHECKERS_FIELDS:
+        assert torch.equal(o1[f], o2[f]), f
+
+
+def test_step_host_matches_device_step():
+    B = 300
+    rng = np.random.default_rng(5)
+    env = VecCheckers(B, **CK2)
+    orc = oracle.OracleCheckers(B, **CK2)
+    env.reset(goals=np.eye(2))
+    orc.reset(np.array([[0, 1]]))
+    for t in range(5):
+        a = rng.integers(0, 5, size=(B, 2)).astype(np.int8)
+        got = env.step_host(a)
+        cmp_fields(got, orc.step(a), gu.CHECKERS_FIELDS, np.float32, "host t=%d" % t)
+
+
+def test_headline_size_properties():
+    """BASELINE config 2 at full size (65 536 envs x 2 agents, max_steps 33): size-independent
+    invariants - cells only ever get collected, counts equal collected cells, rewards sum up,
+    done exactly at max_steps or when the board is clear, and a sampled sub-batch is bit-exact
+    against the oracle."""
+    B, T = 65536, 40
+    env = VecCheckers(B, **CK2)
+    env.reset(goals=np.eye(2))
+    ro = env.rollout(T, actions=None, seed=presets.SEED, record_actions=True)
+    grid = ro["grid"]
+    collected = (grid == 1).sum(dim=(2, 3, 4))        # [T,B]
+    remaining = (grid == -1).sum(dim=(2, 3, 4))
+    assert torch.all(collected + remaining == 24)
+    assert torch.all(collected[1:] >= collected[:-1])
+    counts = ro["vec"][:, :, :, 2:4].sum(dim=(2, 3))
+    assert torch.equal(counts, collected.to(counts.dtype))
+    assert torch.equal(ro["reward"], ro["local_rewards"].double().sum(dim=2).float())
+    vals = torch.unique(ro["local_rewards"])
+    assert set(vals.tolist()) <= {0.0, 1.0, -0.5, float(np.float32(-0.1))}
+    done = ro["done"].bool()
+    steps_done = torch.zeros(T, dtype=torch.bool, device=done.device)
+    steps_done[presets.MAX_STEPS - 1] = True
+    assert torch.equal(done, steps_done[:, None] | (remaining == 0))
+    # sampled envs against the oracle with the recorded actions
+    idx = np.random.default_rng(0).choice(B, 256, replace=False)
+    acts = ro["actions"].cpu().numpy()[:, idx]
+    orc = oracle.OracleCheckers(256, **CK2)
+    orc.reset(np.array([[0, 1]]))
+    for t in range(T):
+        ref = orc.step(acts[t])
+        cmp_fields({f: ro[f][t][idx] for f in gu.CHECKERS_FIELDS}, ref, gu.CHECKERS_FIELDS, np.float32, "t=%d" % t)
+
+
+def test_errors():
+    from cm3_b200 import Cm3Error
+    with pytest.raises(AssertionError):
+        VecCheckers(4, n_rows=4, n_columns=8)
+    with pytest.raises(Cm3Error):
+        VecCheckers(4, n_rows=7, n_columns=30, n_agents=2, agents_r=[0, 2], agents_c=[30, 30])
+    with pytest.raises(Cm3Error):
+        VecCheckers(4, 3, 8, 2, [0, 0], [8, 8], 2, 33)  # same start cell
+    env = VecCheckers(4, **CK2)
+    with pytest.raises(ValueError):
+        env.reset(goals=np.zeros((2, 2)))

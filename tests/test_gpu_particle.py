@@ -1,0 +1,259 @@
+"""GPU parity tests for the particle (multi-goal_spread) kernels through the C ABI.
+Tolerances (BASELINE.json north_star / SURVEY.md H1):
+  float32 kernel, one step from the reference's own state: rtol 1e-5, atol 1e-6
+  float64 kernel, free-running from reset:                 rtol 1e-9, atol 1e-11
+  (float64 differs from NumPy only through exp/log1p/sqrt ulps, amplified by the stiff contact)
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import oracle
+from cm3_b200 import VecParticle, presets
+
+pytestmark = pytest.mark.gpu
+
+F32_RTOL, F32_ATOL = 1e-5, 1e-6
+F64_RTOL, F64_ATOL = 1e-9, 1e-11
+
+
+def cfg_of(fix):
+    return dict(agents_x=fix["cfg_agents_x"], agents_y=fix["cfg_agents_y"],
+                landmarks_x=fix["cfg_landmarks_x"], landmarks_y=fix["cfg_landmarks_y"],
+                initial_std=float(fix["cfg_initial_std"]))
+
+
+def np_of(out):
+    return {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", gu.fixtures("particle"))
+def test_golden_teacher_forced_f32(name):
+    """Every step of every golden trace, started from the reference's own previous state."""
+    fix = gu.load(name)
+    N, K = int(fix["n_agents"]), fix["actions"].shape[0]
+    env = VecParticle(K, N, cfg_of(fix), max_steps=int(fix["max_steps"]))
+    ops = fix["ops"]
+    steps = np.zeros(K, dtype=np.int32)
+    worst = 0.0
+    for s in range(1, len(ops)):
+        if ops[s - 1] == gu.RESET:
+            steps[:] = 0
+        if ops[s] != gu.STEP:
+            continue
+        gs = fix["global_state"][:, s - 1]
+        env.set_state(pos=gs[:, :, 2:4], vel=gs[:, :, 0:2], landmarks=fix["landmarks"][:, s - 1],
+                      steps=steps, collisions=fix["collisions"][:, s - 1])
+        out = np_of(env.step(fix["actions"][:, s]))
+        steps += 1
+        for f in ("global_state", "obs_others", "obs_self", "reward", "reward_n"):
+            np.testing.assert_allclose(out[f], fix[f][:, s], rtol=F32_RTOL, atol=F32_ATOL,
+                                       err_msg="%s op %d %s" % (name, s, f))
+            worst = max(worst, float(np.max(np.abs(out[f] - fix[f][:, s]))))
+        np.testing.assert_array_equal(out["done"], fix["done"][:, s])
+        np.testing.assert_array_equal(env.state["collisions"].cpu().numpy(), fix["collisions"][:, s])
+        reached = env.state["reached"].cpu().numpy()
+        want = (fix["reached"][:, s].astype(np.uint8) << np.arange(N, dtype=np.uint8)).sum(axis=1)
+        np.testing.assert_array_equal(reached, want)
+    print("%s worst abs err %.3g" % (name, worst))
+
+
+@pytest.mark.parametrize("name", gu.fixtures("particle"))
+def test_golden_free_running_f64(name):
+    """float64 state: whole traces from the injected reset state, no teacher forcing."""
+    fix = gu.load(name)
+    N, K = int(fix["n_agents"]), fix["actions"].shape[0]
+    env = VecParticle(K, N, cfg_of(fix), max_steps=int(fix["max_steps"]), dtype=torch.float64)
+    for s, op in enumerate(fix["ops"]):
+        if op == gu.RESET:
+            out = np_of(env.reset(init_pos=fix["global_state"][:, s, :, 2:4], init_landmarks=fix["landmarks"][:, s]))
+            fields = ("global_state", "obs_others", "obs_self", "done")
+        else:
+            out = np_of(env.step(fix["actions"][:, s]))
+            fields = gu.PARTICLE_FIELDS
+        for f in fields:
+            if f == "done":
+                np.testing.assert_array_equal(out[f], fix[f][:, s], err_msg="%s op %d" % (name, s))
+            else:
+                np.testing.assert_allclose(out[f], fix[f][:, s], rtol=F64_RTOL, atol=F64_ATOL,
+                                           err_msg="%s op %d %s" % (name, s, f))
+        np.testing.assert_array_equal(env.state["collisions"].cpu().numpy(), fix["collisions"][:, s])
+
+
+def seek_actions(pos, lm, rng, greedy=0.85):
+    d = lm - pos
+    ax = np.where(d[..., 0] > 0, 2, 1)
+    ay = np.where(d[..., 1] > 0, 4, 3)
+    a = np.where(np.abs(d[..., 0]) >= np.abs(d[..., 1]), ax, ay)
+    rnd = rng.integers(0, 5, size=a.shape)
+    return np.where(rng.random(a.shape) < greedy, a, rnd).astype(np.int8)
+
+
+@pytest.mark.parametrize("N,preset,B", [(4, "antipodal", 4096), (4, "cross", 1000), (2, "merge", 999),
+                                        (1, "stage1", 257), (3, "antipodal", 1001)])
+def test_oracle_teacher_forced_f32_large(N, preset, B):
+    """Teacher-forced against the oracle with goal-seeking actions (many contacts), ragged B."""
+    cfg = presets.PARTICLE[preset]
+    rng = np.random.default_rng(B)
+    orc = oracle.OracleParticle(B, N, max_steps=presets.MAX_STEPS, nthreads=oracle.max_threads())
+    env = VecParticle(B, N, cfg, max_steps=presets.MAX_STEPS)
+    pos = np.tile(np.stack([cfg["agents_x"][:N], cfg["agents_y"][:N]], axis=1), (B, 1, 1)) + rng.normal(0, 0.05, (B, N, 2))
+    lm = np.tile(np.stack([cfg["landmarks_x"][:N], cfg["landmarks_y"][:N]], axis=1), (B, 1, 1)).astype(np.float64)
+    ref = orc.reset_to(pos, lm)
+    out = np_of(env.reset(init_pos=pos, init_landmarks=lm))
+    for f in ("global_state", "obs_others", "obs_self"):
+        np.testing.assert_allclose(out[f], ref[f], rtol=F32_RTOL, atol=F32_ATOL)
+    n_contacts = 0
+    for t in range(45):
+        st = orc.get_state()
+        # inject float32-rounded state into BOTH so they start the step from identical numbers
+        p32 = st["pos"].astype(np.float32).astype(np.float64)
+        v32 = st["vel"].astype(np.float32).astype(np.float64)
+        orc.set_state(pos=p32, vel=v32)
+        env.set_state(pos=p32, vel=v32, steps=st["steps"], collisions=st["collisions"])
+        a = seek_actions(p32, lm, rng)
+        ref = orc.step(a)
+        out = np_of(env.step(a))
+        for f in ("global_state", "obs_others", "obs_self", "reward", "reward_n"):
+            np.testing.assert_allclose(out[f], ref[f], rtol=F32_RTOL, atol=F32_ATOL, err_msg="t=%d %s" % (t, f))
+        # done / collisions can legitimately flip only when a distance sits within float32
+        # rounding of a threshold; require agreement wherever the oracle is not borderline
+        st2 = orc.get_state()
+        n_contacts += int((st2["collisions"] - st["collisions"]).sum())
+        agree = (out["done"] == ref["done"]).mean()
+        assert agree > 0.999, agree
+    assert N == 1 or n_contacts > 0
+
+
+def test_rollout_equals_stepping_f32():
+    B, N, T = 2048, 4, 40
+    cfg = presets.PARTICLE["antipodal"]
+    rng = np.random.default_rng(1)
+    actions = rng.integers(0, 5, size=(T, B, N)).astype(np.int8)
+    e1 = VecParticle(B, N, cfg, max_steps=presets.MAX_STEPS)
+    e2 = VecParticle(B, N, cfg, max_steps=presets.MAX_STEPS)
+    e1.reset(); e2.reset()
+    ro = e1.rollout(T, actions=actions)
+    for t in range(T):
+        out = e2.step(actions[t])
+        for f in gu.PARTICLE_FIELDS:
+            assert torch.equal(out[f], ro[f][t]), (t, f)
+    for k in e1.state:
+        assert torch.equal(e1.state[k], e2.state[k]), k
+
+
+def test_free_running_f64_vs_oracle_headline_config():
+    """PA4 preset, 4096 envs, goal-seeking -> crossing at the centre; float64 free-running."""
+    B, N, T = 4096, 4, 50
+    cfg = presets.PARTICLE["antipodal"]
+    rng = np.random.default_rng(2)
+    orc = oracle.OracleParticle(B, N, max_steps=T, nthreads=oracle.max_threads())
+    env = VecParticle(B, N, cfg, max_steps=T, dtype=torch.float64)
+    pos = np.tile(np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1), (B, 1, 1)) + rng.normal(0, 0.02, (B, N, 2))
+    lm = np.tile(np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1), (B, 1, 1)).astype(np.float64)
+    orc.reset_to(pos, lm)
+    env.reset(init_pos=pos, init_landmarks=lm)
+    for t in range(T):
+        a = seek_actions(orc.get_state()["pos"], lm, rng)
+        ref = orc.step(a)
+        out = np_of(env.step(a))
+        for f in ("global_state", "reward_n", "reward"):
+            np.testing.assert_allclose(out[f], ref[f], rtol=1e-7, atol=1e-9, err_msg="t=%d %s" % (t, f))
+    assert orc.get_state()["collisions"].sum() > 0
+    np.testing.assert_array_equal(env.state["collisions"].cpu().numpy(), orc.get_state()["collisions"])
+
+
+def test_device_reset_presets_and_determinism():
+    B, N = 4096, 4
+    cfg = presets.PARTICLE["antipodal"]
+    env = VecParticle(B, N, cfg, prob_random=0.0, max_steps=presets.MAX_STEPS)
+    out = env.reset(seed=1)
+    want = np.stack([np.zeros(4), np.zeros(4), cfg["agents_x"], cfg["agents_y"]], axis=1).astype(np.float32)
+    np.testing.assert_array_equal(out["global_state"].cpu().numpy(), np.tile(want, (B, 1, 1)))
+    lm = np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1).astype(np.float32)
+    np.testing.assert_array_equal(env.state["landmarks"].cpu().numpy(), np.tile(lm, (B, 1, 1)))
+    # first step from the presets reproduces SURVEY §8c anchor values of the reference
+    out = env.step(np.tile(np.array([2, 1, 2, 1], dtype=np.int8), (B, 1)))
+    np.testing.assert_allclose(out["global_state"][0, 0].cpu().numpy(), [0.5, 0, -0.85, -0.9], rtol=1e-6)
+    np.testing.assert_allclose(out["reward_n"][0].cpu().numpy(), [-2.5104780421266386] * 4, rtol=1e-6)
+    np.testing.assert_allclose(float(out["reward"][0]), -10.041912168506554, rtol=1e-6)
+
+
+def test_device_reset_random_distribution_and_shard_invariance():
+    """prob_random / initial_std draws (multi-goal_spread.py:75-91 on Philox): distribution-level
+    checks, reproducibility, and independence from how the batch is sharded."""
+    B, N = 65536, 2
+    cfg = presets.PARTICLE["merge"]  # initial_std 0.05
+    env = VecParticle(B, N, cfg, prob_random=0.2, max_steps=presets.MAX_STEPS)
+    env.reset(seed=presets.SEED, reset_counter=3)
+    sv = env.state["sv"].cpu().numpy().astype(np.float64)
+    lm = env.state["landmarks"].cpu().numpy().astype(np.float64)
+    preset_lm = np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1)
+    is_rand = np.any(np.abs(lm - preset_lm) > 1e-6, axis=(1, 2))
+    assert abs(is_rand.mean() - 0.2) < 0.01
+    assert np.all(sv[:, :, 0:2] == 0)
+    pr = sv[is_rand][:, :, 2:4]
+    assert pr.min() >= -1 and pr.max() < 1
+    assert abs(pr.mean()) < 0.02 and abs(pr.var() - 1 / 3) < 0.02
+    jit = sv[~is_rand][:, :, 2:4] - np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1)
+    assert abs(jit.mean()) < 2e-3 and abs(jit.std() - 0.05) < 2e-3
+    from scipy import stats
+    assert stats.kstest(jit.ravel()[:20000] / 0.05, "norm").pvalue > 1e-3
+    half = VecParticle(B // 2, N, cfg, prob_random=0.2, max_steps=presets.MAX_STEPS, env_id_offset=B // 2)
+    half.reset(seed=presets.SEED, reset_counter=3)
+    assert torch.equal(half.state["sv"], env.state["sv"][B // 2:])
+    assert torch.equal(half.state["landmarks"], env.state["landmarks"][B // 2:])
+
+
+def test_auto_reset_and_philox_rollout_properties():
+    B, N, T = 65536, 4, 70
+    cfg = presets.PARTICLE["antipodal"]
+    env = VecParticle(B, N, cfg, max_steps=presets.MAX_STEPS)
+    first = env.reset()["global_state"].clone()
+    ro = env.rollout(T, actions=None, seed=presets.SEED, auto_reset=True, record_actions=True)
+    acts = ro["actions"].cpu().numpy()
+    np.testing.assert_array_equal(acts[:, :1024], oracle.philox_actions(presets.SEED, 0, 1024, N, 0, T))
+    done = ro["done"].cpu().numpy()
+    assert done[presets.MAX_STEPS - 1].all() and done[2 * presets.MAX_STEPS - 1].all()
+    assert done.sum() == 2 * B  # random walks never reach the antipodal landmarks in 33 steps
+    assert torch.equal(ro["global_state"][presets.MAX_STEPS - 1], first)
+    # obs_self is global_state; reward = sum(reward_n); finite everywhere
+    assert torch.equal(ro["obs_self"], ro["global_state"])
+    assert torch.isfinite(ro["obs_others"]).all()
+    np.testing.assert_allclose(ro["reward"].cpu().numpy(), ro["reward_n"].cpu().numpy().astype(np.float64).sum(-1), rtol=1e-6)
+    # sampled envs, float32 free-running vs oracle over the first episode: reported drift
+    idx = np.random.default_rng(0).choice(B, 512, replace=False)
+    orc = oracle.OracleParticle(512, N, max_steps=presets.MAX_STEPS)
+    pos = np.tile(np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1), (512, 1, 1))
+    lm = np.tile(np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1), (512, 1, 1)).astype(np.float64)
+    orc.reset_to(pos, lm)
+    gs = ro["global_state"].cpu().numpy()
+    drift = 0.0
+    for t in range(presets.MAX_STEPS - 1):
+        ref = orc.step(acts[t][idx])
+        drift = max(drift, float(np.abs(gs[t][idx] - ref["global_state"]).max()))
+    assert drift < 1e-4, drift  # collision-free random walks stay ~1e-6
+
+
+def test_step_host_and_masked_reset():
+    B, N = 300, 4
+    cfg = presets.PARTICLE["cross"]
+    env = VecParticle(B, N, cfg, max_steps=presets.MAX_STEPS)
+    env.reset()
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 5, size=(B, N)).astype(np.int8)
+    sd = env.state_dict()
+    dev = {k: v.clone() for k, v in env.step(a).items()}
+    env.load_state_dict(sd)
+    host = env.step_host(a)
+    for f in gu.PARTICLE_FIELDS:
+        np.testing.assert_array_equal(host[f], dev[f].cpu().numpy())
+    mask = (rng.random(B) < 0.5).astype(np.uint8)
+    before = env.state["sv"].clone()
+    env.reset(mask=mask)
+    after = env.state["sv"]
+    m = torch.as_tensor(mask, device=after.device).bool()
+    assert torch.equal(after[~m], before[~m])
+    assert torch.all(after[m][:, :, 0:2] == 0)
+    assert torch.all(env.state["steps"][m] == 0) and torch.all(env.state["steps"][~m] == 1)
