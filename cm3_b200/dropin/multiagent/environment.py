@@ -1,0 +1,199 @@
+"""Drop-in for multiagent/environment.py's MultiAgentEnv: same constructor, reset() 4-tuple
+(environment.py:149) and step(action_n) 6-tuple (environment.py:123), for the multi-goal_spread
+scenario.  One fused CUDA launch per step (B = 1, float64 state and outputs)."""
+import numpy as np
+
+
+class _Discrete(object):
+    """Stand-in for gym.spaces.Discrete (only .n is ever read, environment.py:46,61-62)."""
+    def __init__(self, n):
+        self.n = n
+
+
+class _Box(object):
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+
+class MultiAgentEnv(object):
+    metadata = {'render.modes': ['human', 'rgb_array']}
+
+    def __init__(self, world, reset_callback=None, reward_callback=None,
+                 observation_callback=None, info_callback=None,
+                 done_callback=None, shared_viewer=True, max_steps=50, device="cuda:0"):
+        import torch
+        from cm3_b200.vec_particle import VecParticle
+        self.world = world
+        self.agents = self.world.policy_agents
+        self.n = len(world.policy_agents)
+        self.reset_callback = reset_callback
+        self.reward_callback = reward_callback
+        self.observation_callback = observation_callback
+        self.info_callback = info_callback
+        self.done_callback = done_callback
+        self.discrete_action_space = True
+        self.discrete_action_input = True
+        self.force_discrete_action = world.discrete_action if hasattr(world, 'discrete_action') else False
+        self.shared_reward = world.collaborative if hasattr(world, 'collaborative') else False
+        self.time = 0
+        self.max_steps = max_steps
+        self.steps = 0
+
+        scenario = getattr(world, "_cm3_scenario", None)
+        callbacks_ok = scenario is not None and all(
+            cb is None or getattr(cb, "__self__", None) is scenario
+            for cb in (reset_callback, reward_callback, observation_callback, done_callback))
+        if not callbacks_ok or reset_callback is None or reward_callback is None or \
+                observation_callback is None or done_callback is None:
+            raise NotImplementedError(
+                "cm3_b200's MultiAgentEnv runs the multi-goal_spread callbacks as one fused CUDA "
+                "kernel; pass scenario.reset_world / reward / observation / done of a Scenario "
+                "loaded with multiagent.scenarios.load('multi-goal_spread.py')")
+        if self.shared_reward:
+            raise NotImplementedError("world.collaborative=True is not used by multi-goal_spread")
+        self.scenario = scenario
+
+        # spaces (environment.py:39-71); obs_dim probed through the callback like the reference
+        self.action_space = []
+        self.observation_space = []
+        for agent in self.agents:
+            self.action_space.append(_Discrete(world.dim_p * 2 + 1))
+            obs_dim = len(observation_callback(agent, self.world))
+            self.observation_space.append(_Box(-np.inf, +np.inf, (obs_dim,), np.float32))
+            agent.action.c = np.zeros(self.world.dim_c)
+
+        overrides = dict(dt=world.dt, damping=world.damping, contact_force=world.contact_force,
+                         contact_margin=world.contact_margin, agent_size=world.agents[0].size,
+                         mass=world.agents[0].mass)
+        self._vec = VecParticle(1, self.n, scenario.config, prob_random=scenario.prob_random,
+                                max_steps=max_steps, device=device, dtype=torch.float64, **overrides)
+        self._results = None
+        self._synced = None
+        scenario._env = self
+        self._upload_world()   # make_world() already drew an initial state (multi-goal_spread.py:62)
+
+        self.shared_viewer = shared_viewer
+        self.viewers = [None] if shared_viewer else [None] * self.n
+        self._reset_render()
+
+    # ------------------------------------------------------------------ host <-> device sync
+    def _host_arrays(self):
+        pos = np.array([a.state.p_pos for a in self.world.agents], dtype=np.float64)
+        vel = np.array([a.state.p_vel for a in self.world.agents], dtype=np.float64)
+        lm = np.array([l.state.p_pos for l in self.world.landmarks], dtype=np.float64)
+        return pos, vel, lm
+
+    def _upload_world(self):
+        """Host entity objects -> device state (after reset_world or a manual edit)."""
+        pos, vel, lm = self._host_arrays()
+        reached = np.array([[bool(a.reached) for a in self.world.agents]], dtype=np.uint8)
+        self._vec.set_state(pos=pos[None], vel=vel[None], landmarks=lm[None],
+                            steps=np.array([self.steps]), collisions=np.array([self.scenario.collisions]),
+                            reached=reached)
+        self._synced = (pos, vel, lm)
+        self._results = None
+
+    def _world_was_reset(self):
+        self._synced = None
+        self._results = None
+
+    def _ensure_synced(self):
+        pos, vel, lm = self._host_arrays()
+        if self._synced is None or not all(np.array_equal(a, b) for a, b in zip((pos, vel, lm), self._synced)):
+            self._upload_world()
+
+    def _download(self, out, with_reward):
+        fields = ("global_state", "obs_others", "obs_self", "done") + (("reward", "reward_n") if with_reward else ())
+        res = {f: out[f].cpu().numpy()[0] for f in fields}
+        if not with_reward:
+            res["reward"] = res["reward_n"] = None
+        gs = res["global_state"]
+        for i, agent in enumerate(self.world.agents):
+            agent.state.p_vel = gs[i, 0:2].copy()
+            agent.state.p_pos = gs[i, 2:4].copy()
+        reached = int(self._vec.state["reached"].cpu().numpy()[0])
+        for i, agent in enumerate(self.world.agents):
+            agent.reached = bool((reached >> i) & 1)
+        self.scenario.collisions = int(self._vec.state["collisions"].cpu().numpy()[0])
+        self._synced = self._host_arrays()
+        self._results = res
+        return res
+
+    def _current_results(self):
+        """Results for the scenario callbacks: the last launch's, or a fresh observe-only launch
+        when the host state changed since."""
+        pos, vel, lm = self._host_arrays()
+        stale = self._results is None or self._synced is None or \
+            not all(np.array_equal(a, b) for a, b in zip((pos, vel, lm), self._synced))
+        if stale:
+            keep = self._results
+            self._upload_world()
+            out = self._vec.reset(mask=np.zeros(1, dtype=np.uint8))  # observe only
+            res = self._download(out, with_reward=False)
+            if keep is not None and keep.get("reward_n") is not None:
+                res["reward"], res["reward_n"] = keep["reward"], keep["reward_n"]
+        return self._results
+
+    # ------------------------------------------------------------------ reference API
+    def step(self, action_n):
+        """-> (global_state [N,4], obs_others_n, obs_n, reward, reward_n, done), environment.py:123"""
+        self.agents = self.world.policy_agents
+        self._ensure_synced()
+        a = np.zeros((1, self.n), dtype=np.int64)
+        for i in range(self.n):
+            a[0, i] = int(action_n[i])
+        out = self._vec.step(a)
+        self.steps += 1
+        res = self._download(out, with_reward=True)
+        obs_n, obs_others_n, reward_n, done_n = [], [], [], []
+        for agent in self.agents:   # callback order of environment.py:95-104
+            obs_self, obs_others = self._get_obs(agent)
+            obs_n.append(obs_self)
+            obs_others_n.append(obs_others)
+            reward_n.append(self._get_reward(agent))
+            done_n.append(self._get_done(agent))
+        reward = np.float64(res["reward"])   # np.sum(reward_n), evaluated on the device in index order
+        global_state = res["global_state"].copy()
+        done = bool(res["done"])
+        assert done == (self.steps == self.max_steps or bool(np.all(done_n)))
+        return global_state, obs_others_n, obs_n, reward, reward_n, done
+
+    def reset(self):
+        """-> (global_state, obs_others_n, obs_n, done), environment.py:149"""
+        self.reset_callback(self.world)      # host RNG draws, like the reference
+        self._reset_render()
+        self.steps = 0
+        self._upload_world()
+        pos, vel, lm = self._synced
+        out = self._vec.reset(init_pos=pos[None], init_landmarks=lm[None])
+        res = self._download(out, with_reward=False)
+        obs_n, obs_others_n, done_n = [], [], []
+        self.agents = self.world.policy_agents
+        for agent in self.agents:
+            obs_self, obs_others = self._get_obs(agent)
+            obs_n.append(obs_self)
+            obs_others_n.append(obs_others)
+            done_n.append(self._get_done(agent))
+        return res["global_state"].copy(), obs_others_n, obs_n, np.any(done_n)
+
+    def _get_info(self, agent):
+        if self.info_callback is None:
+            return {}
+        return self.info_callback(agent, self.world)
+
+    def _get_obs(self, agent):
+        return self.observation_callback(agent, self.world)
+
+    def _get_done(self, agent):
+        return self.done_callback(agent, self.world)
+
+    def _get_reward(self, agent):
+        return self.reward_callback(agent, self.world)
+
+    def _reset_render(self):
+        self.render_geoms = None
+        self.render_geoms_xform = None
+
+    def render(self, mode='human'):
+        raise NotImplementedError("rendering (pyglet) is out of scope; every training path of the "
+                                  "reference runs with render=False (train_onpolicy.py:394)")

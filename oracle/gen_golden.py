@@ -193,6 +193,7 @@ def gen_particle(MAE, scenarios, name, n_agents, cfg, prob_random, max_steps, K,
     for key in ("agents_x", "agents_y", "landmarks_x", "landmarks_y"):
         fix["cfg_" + key] = np.array(cfg[key], dtype=np.float64)
     fix["cfg_initial_std"] = np.float64(cfg["initial_std"])
+    fix["global_rng_seed"] = np.int64(seed)  # np.random.seed / random.seed before trace 0
     return name, fix
 
 
