@@ -5,6 +5,7 @@ import os
 from .build import library_path
 
 MAX_AGENTS = 4
+MAX_DST = 8
 REAL_F32, REAL_F64 = 0, 1
 
 STATUS_NAMES = {0: "CM3_OK", -1: "CM3_ERR_BAD_ARG", -2: "CM3_ERR_BAD_SHAPE", -3: "CM3_ERR_CUDA",
@@ -71,6 +72,9 @@ SYMBOLS = {
                                     C.POINTER(CheckersOutputs), _vp]),
     "cm3_checkers_rollout": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _u64, _i64, _i32, _i32,
                                        _vp, C.POINTER(CheckersOutputs), _vp]),
+    "cm3_checkers_rollout_gather": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _u64, _i64, _i32,
+                                              _i32, _vp, _i32, C.POINTER(CheckersOutputs), _i64,
+                                              _i64, _vp]),
     "cm3_checkers_step_host": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
                                          C.POINTER(CheckersOutputs), C.POINTER(CheckersOutputs),
                                          _vp]),
@@ -83,6 +87,9 @@ SYMBOLS = {
                                     C.POINTER(ParticleOutputs), _vp]),
     "cm3_particle_rollout": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _u64, _i64, _i32, _i32,
                                        _vp, C.POINTER(ParticleOutputs), _vp]),
+    "cm3_particle_rollout_gather": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _u64, _i64, _i32,
+                                              _i32, _vp, _i32, C.POINTER(ParticleOutputs), _i64,
+                                              _i64, _vp]),
     "cm3_particle_step_host": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp,
                                          C.POINTER(ParticleOutputs), C.POINTER(ParticleOutputs),
                                          _vp]),

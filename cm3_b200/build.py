@@ -4,14 +4,20 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+# (source, extra defines, object suffix): checkers.cu is compiled once per arithmetic type so the
+# two halves of its template instantiations build in parallel
+UNITS = [("api.cu", (), "api"), ("particle.cu", (), "particle"),
+         ("checkers.cu", ("CM3_CK_REAL=0",), "checkers_f32"),
+         ("checkers.cu", ("CM3_CK_REAL=1",), "checkers_f64")]
 SOURCES = ["api.cu", "checkers.cu", "particle.cu"]
 HEADERS = ["common.cuh", "params.cuh", os.path.join("..", "..", "include", "cm3env.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def library_path():
-    return os.path.join(CSRC, "libcm3env.so")
+    """The in-tree library; CM3ENV_LIBRARY selects an experimental build (tools/build_variants.py)."""
+    return os.environ.get("CM3ENV_LIBRARY") or os.path.join(CSRC, "libcm3env.so")
 
 
 def _nvcc():
@@ -29,11 +35,24 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build_library(force=False, verbose=False):
-    """Compile every CUDA source into one shared library; returns its path."""
-    if not force and not is_stale():
-        return library_path()
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", library_path()] + [os.path.join(CSRC, f) for f in SOURCES]
-    subprocess.check_call(cmd)
-    return library_path()
+def build_library(force=False, verbose=False, defines=(), output=None):
+    """Compile every CUDA source for sm_100a and link one shared library; returns its path.
+    `defines` / `output` build an experimental variant next to the default library."""
+    out = output or library_path()
+    if not force and not defines and not is_stale():
+        return out
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(CSRC, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src, unit_defs, name in UNITS:
+        obj = os.path.join(objdir, name + ".o")
+        objs.append(obj)
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-D%s" % d for d in tuple(defines) + tuple(unit_defs)] + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    subprocess.check_call([_nvcc()] + ARCH_FLAGS + ["-shared", "-o", out] + objs)
+    return out

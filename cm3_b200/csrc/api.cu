@@ -2,6 +2,8 @@
 // Handles hold configuration only; every buffer is the caller's (see the header).
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -54,6 +56,14 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_PDL");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
 static size_t real_size(int real) { return real == CM3_REAL_F64 ? 8 : 4; }
 
 }  // namespace cm3
@@ -68,6 +78,44 @@ struct cm3_particle_s {
     cm3_particle_config cfg;
     PtParams base;
 };
+
+static CkOut ck_out(const cm3_checkers_outputs &o) {
+    return CkOut{(char *)o.grid, (char *)o.vec, (char *)o.obs_others, (char *)o.obs_self_t, (char *)o.obs_self_v,
+                 (char *)o.reward, (char *)o.local_rewards, o.done};
+}
+
+// rollout_gather: n_dst destination sets with identical NULL patterns, this shard at rows
+// [dst_env0, dst_env0 + B) of [T][dst_B][...]
+template <typename Out, typename POut, typename Conv>
+static int fill_destinations(int32_t n_dst, const Out *dsts, int64_t dst_B, int64_t dst_env0, int B,
+                             POut *out, int &n_out, long long &out_B, long long &out_env0, Conv conv) {
+    if (n_dst < 1 || n_dst > CM3_MAX_DST || !dsts) {
+        set_error("n_dst must be 1..%d and dsts non-NULL", CM3_MAX_DST);
+        return CM3_ERR_BAD_ARG;
+    }
+    if (dst_env0 < 0 || dst_B < dst_env0 + B) {
+        set_error("destination rows [%lld, %lld) do not fit dst_B=%lld", (long long)dst_env0,
+                  (long long)(dst_env0 + B), (long long)dst_B);
+        return CM3_ERR_BAD_ARG;
+    }
+    const void *const *first = reinterpret_cast<const void *const *>(&dsts[0]);
+    for (int d = 0; d < n_dst; ++d) {
+        const void *const *f = reinterpret_cast<const void *const *>(&dsts[d]);
+        for (size_t i = 0; i < sizeof(Out) / sizeof(void *); ++i)
+            if ((f[i] == nullptr) != (first[i] == nullptr)) {
+                set_error("destination %d differs from destination 0 in which fields are NULL", d);
+                return CM3_ERR_BAD_ARG;
+            }
+        out[d] = conv(dsts[d]);
+    }
+    n_out = n_dst; out_B = dst_B; out_env0 = dst_env0;
+    return CM3_OK;
+}
+
+static PtOut pt_out(const cm3_particle_outputs &o) {
+    return PtOut{(char *)o.global_state, (char *)o.obs_others, (char *)o.obs_self, (char *)o.reward,
+                 (char *)o.reward_n, o.done};
+}
 
 extern "C" {
 
@@ -160,12 +208,8 @@ static int ck_fill(cm3_checkers_t h, const cm3_checkers_state *st, const cm3_che
     }
     p = h->base;
     p.remaining = st->remaining; p.agents = st->agents; p.meta = st->meta;
-    if (outs) {
-        p.grid = (char *)outs->grid; p.vec = (char *)outs->vec; p.obs_others = (char *)outs->obs_others;
-        p.obs_self_t = (char *)outs->obs_self_t; p.obs_self_v = (char *)outs->obs_self_v;
-        p.reward = (char *)outs->reward; p.local_rewards = (char *)outs->local_rewards;
-        p.done = outs->done;
-    }
+    p.n_dst = 1; p.out_B = p.B; p.out_env0 = 0;
+    if (outs) p.out[0] = ck_out(*outs);
     return CM3_OK;
 }
 
@@ -183,7 +227,7 @@ int cm3_checkers_reset(cm3_checkers_t h, const cm3_checkers_state *st, const uin
     if (rc != CM3_OK) return rc;
     p.mode = 1; p.T = 1;
     p.goal_idx = goal_idx; p.env_mask = env_mask;
-    p.reward = nullptr; p.local_rewards = nullptr;
+    p.out[0].reward = nullptr; p.out[0].local_rewards = nullptr;
     return ck_launch(h, p, stream);
 }
 
@@ -194,6 +238,22 @@ int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const i
     int rc = ck_fill(h, st, outs, p);
     if (rc != CM3_OK) return rc;
     if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
+    p.actions = actions; p.actions_out = actions_out;
+    p.seed = seed; p.t0 = t0;
+    return ck_launch(h, p, stream);
+}
+
+int cm3_checkers_rollout_gather(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                                uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset, int8_t *actions_out,
+                                int32_t n_dst, const cm3_checkers_outputs *dsts, int64_t dst_B,
+                                int64_t dst_env0, void *stream) {
+    CkParams p;
+    int rc = ck_fill(h, st, nullptr, p);
+    if (rc != CM3_OK) return rc;
+    if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    rc = fill_destinations(n_dst, dsts, dst_B, dst_env0, p.B, p.out, p.n_dst, p.out_B, p.out_env0, ck_out);
+    if (rc != CM3_OK) return rc;
     p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions; p.actions_out = actions_out;
     p.seed = seed; p.t0 = t0;
@@ -288,6 +348,22 @@ int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
         p.landmarks_x[i] = cfg->landmarks_x[i]; p.landmarks_y[i] = cfg->landmarks_y[i];
     }
     p.initial_std = cfg->initial_std; p.prob_random = cfg->prob_random;
+    // Exact shortcuts of the step kernel (particle.cu): with x = -(dist - dist_min)/contact_margin
+    // (core.py:191), expf(x) == 0 for x <= -110 and exp(x) == 0 for x <= -760, so the contact
+    // force of a pair further apart than dist_min + 110 k (760 k) is exactly +-0.  2 % headroom
+    // covers the rounding of the squared distance.  Degenerate constants disable the shortcut.
+    const double k = cfg->contact_margin;
+    const bool sane = k > 0.0 && std::isfinite(k) && p.dist_min >= 0.0 && std::isfinite(p.dist_min) &&
+                      std::isfinite(cfg->contact_force);
+    const double inf = HUGE_VAL;
+    const double far2_f32 = sane ? std::pow((p.dist_min + 110.0 * k) * 1.02, 2) : inf;
+    const double far2_f64 = sane ? std::pow((p.dist_min + 760.0 * k) * 1.02, 2) : inf;
+    const double near2 = (p.dist_min >= 0.0 && std::isfinite(p.dist_min)) ? std::pow(p.dist_min * 1.01, 2) + 1e-30 : inf;
+    p.kd = PtConsts<double>{p.dt, 1.0 - p.damping, p.contact_force, p.contact_margin, p.dist_min, p.mass,
+                            p.sensitivity, -p.reach_thresh, far2_f64, near2};
+    p.kf = PtConsts<float>{(float)p.dt, (float)(1.0 - p.damping), (float)p.contact_force, (float)p.contact_margin,
+                           (float)p.dist_min, (float)p.mass, (float)p.sensitivity, (float)(-p.reach_thresh),
+                           (float)far2_f32, (float)near2};
     *out = h;
     return CM3_OK;
 }
@@ -307,11 +383,8 @@ static int pt_fill(cm3_particle_t h, const cm3_particle_state *st, const cm3_par
     p = h->base;
     p.sv = (char *)st->sv; p.landmarks = (char *)st->landmarks;
     p.steps = st->steps; p.collisions = st->collisions; p.reached = st->reached;
-    if (outs) {
-        p.global_state = (char *)outs->global_state; p.obs_others = (char *)outs->obs_others;
-        p.obs_self = (char *)outs->obs_self; p.reward = (char *)outs->reward;
-        p.reward_n = (char *)outs->reward_n; p.done = outs->done;
-    }
+    p.n_dst = 1; p.out_B = p.B; p.out_env0 = 0;
+    if (outs) p.out[0] = pt_out(*outs);
     return CM3_OK;
 }
 
@@ -334,7 +407,7 @@ int cm3_particle_reset(cm3_particle_t h, const cm3_particle_state *st, const voi
     p.mode = 1; p.T = 1;
     p.init_pos = (const char *)init_pos; p.init_landmarks = (const char *)init_landmarks;
     p.env_mask = env_mask; p.seed = seed; p.reset_counter = reset_counter;
-    p.reward = nullptr; p.reward_n = nullptr;
+    p.out[0].reward = nullptr; p.out[0].reward_n = nullptr;
     return pt_launch(h, p, stream);
 }
 
@@ -345,6 +418,21 @@ int cm3_particle_rollout(cm3_particle_t h, const cm3_particle_state *st, const i
     int rc = pt_fill(h, st, outs, p);
     if (rc != CM3_OK) return rc;
     if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
+    p.actions = actions; p.actions_out = actions_out; p.seed = seed; p.t0 = t0;
+    return pt_launch(h, p, stream);
+}
+
+int cm3_particle_rollout_gather(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                                uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset, int8_t *actions_out,
+                                int32_t n_dst, const cm3_particle_outputs *dsts, int64_t dst_B,
+                                int64_t dst_env0, void *stream) {
+    PtParams p;
+    int rc = pt_fill(h, st, nullptr, p);
+    if (rc != CM3_OK) return rc;
+    if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    rc = fill_destinations(n_dst, dsts, dst_B, dst_env0, p.B, p.out, p.n_dst, p.out_B, p.out_env0, pt_out);
+    if (rc != CM3_OK) return rc;
     p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions; p.actions_out = actions_out; p.seed = seed; p.t0 = t0;
     return pt_launch(h, p, stream);

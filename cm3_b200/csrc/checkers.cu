@@ -24,9 +24,18 @@
 #include "common.cuh"
 #include "params.cuh"
 
+#ifndef CM3_CK_REAL
+#error "compile with -DCM3_CK_REAL=0 (float kernels) and -DCM3_CK_REAL=1 (double kernels)"
+#endif
+
 namespace cm3 {
 
-constexpr int kCkWarpsPerBlock = 2;
+// One warp per block: with 14 KB of staging per warp 16 blocks fit an SM, so the 2048 tiles of the
+// 65 536-env headline batch are resident in a single wave (measured: +7 % over 2 warps per block).
+#ifndef CM3_CK_WPB
+#define CM3_CK_WPB 1
+#endif
+constexpr int kCkWarpsPerBlock = CM3_CK_WPB;
 
 template <typename Real> __device__ __forceinline__ Real tri_value(uint32_t nz, uint32_t neg);
 // value in {0, +1, -1}: nz = cell is non-zero, neg = cell is -1 (neg implies nz)
@@ -101,6 +110,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     constexpr int EW = Gm::EW;
     constexpr uint32_t CM = Gm::CM;
 
+    pdl_launch_dependents();  // the next step's grid may become resident while this one drains
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *lut_row = reinterpret_cast<Real *>(smem_raw);
     Real *lut_col = lut_row + TR;
@@ -122,6 +132,8 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     const int nenv = min(EW, p.B - env0);
     const bool valid = (a < N) && (e < nenv);
     const size_t B = (size_t)p.B;
+
+    pdl_wait();  // state written by the previous launch is visible from here on
 
     // ---- load compact state
     uint64_t rem = 0;
@@ -154,15 +166,17 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     bool pending = false;  // bulk stores of this warp whose smem source may still be in flight
 
     // Expands the observations of the current state into the outputs of time slot t.
+    const CkOut &o0 = p.out[0];
+    const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
     auto emit = [&](int t) {
-        const size_t slot = (size_t)t * B;
+        const size_t slot = (size_t)t * OB + oe0;
         const int my_r = pick<N>(ar, a), my_c = pick<N>(ac, a);
         if (pending) {
             if (lane < 2) bulk_wait_read();
         }
         __syncwarp();
         // ---------------- window of agent a (get_obs, checkers.py:97-109)
-        if (p.obs_self_t != nullptr && valid) {
+        if (o0.obs_self_t != nullptr && valid) {
             Real *win = stage_win + (e * N + a) * WW3;
             const int sh = my_c - O;  // leftmost window column, >= 0
 #pragma unroll
@@ -194,8 +208,25 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 }
             }
         }
+        // the window tile (3/4 of the bytes) leaves first and drains while the rest is expanded
+        pending = false;
+        if (o0.obs_self_t != nullptr) {
+            fence_proxy_async();
+            __syncwarp();
+            const uint32_t bytes = (uint32_t)(nenv * N * WW3 * sizeof(Real));
+            for (int d = 0; d < p.n_dst; ++d) {
+                Real *g = reinterpret_cast<Real *>(p.out[d].obs_self_t) + (slot + env0) * (size_t)(N * WW3);
+                if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
+                    if (lane == 0) bulk_store(g, stage_win, bytes);
+                    pending = true;
+                } else {
+                    for (int idx = lane; idx < nenv * N * WW3; idx += kWarp) g[idx] = stage_win[idx];
+                }
+            }
+            if (lane == 0) bulk_commit();
+        }
         // ---------------- global grid (get_valid_grid, :66-76): lane a writes channel a
-        if (p.grid != nullptr && valid && a < 2) {
+        if (o0.grid != nullptr && valid && a < 2) {
             Real *gr = stage_grid + e * G;
 #pragma unroll
             for (int i = 0; i < R; ++i) {
@@ -217,45 +248,40 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         }
         fence_proxy_async();
         __syncwarp();
-        pending = false;
-        if (p.obs_self_t != nullptr) {
-            Real *g = reinterpret_cast<Real *>(p.obs_self_t) + (slot + env0) * (size_t)(N * WW3);
-            const uint32_t bytes = (uint32_t)(nenv * N * WW3 * sizeof(Real));
-            if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
-                if (lane == 0) { bulk_store(g, stage_win, bytes); bulk_commit(); }
-                pending = true;
-            } else {
-                for (int idx = lane; idx < nenv * N * WW3; idx += kWarp) g[idx] = stage_win[idx];
-            }
-        }
-        if (p.grid != nullptr) {
-            Real *g = reinterpret_cast<Real *>(p.grid) + (slot + env0) * (size_t)G;
+        if (o0.grid != nullptr) {
             const uint32_t bytes = (uint32_t)(nenv * G * sizeof(Real));
-            if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
-                if (lane == 1) { bulk_store(g, stage_grid, bytes); bulk_commit(); }
-                pending = true;
-            } else {
-                for (int idx = lane; idx < nenv * G; idx += kWarp) g[idx] = stage_grid[idx];
+            for (int d = 0; d < p.n_dst; ++d) {
+                Real *g = reinterpret_cast<Real *>(p.out[d].grid) + (slot + env0) * (size_t)G;
+                if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
+                    if (lane == 1) bulk_store(g, stage_grid, bytes);
+                    pending = true;
+                } else {
+                    for (int idx = lane; idx < nenv * G; idx += kWarp) g[idx] = stage_grid[idx];
+                }
             }
+            if (lane == 1) bulk_commit();
         }
         // ---------------- small per-agent vectors, straight from registers
         if (valid) {
             const size_t rec = (slot + env) * N + a;
             const int my_g = pick<N>(ng, a), my_o = pick<N>(no, a);
-            if (p.vec != nullptr)  // get_global_state, :89-93
-                store4<Real>(reinterpret_cast<Real *>(p.vec) + rec * 4, (Real)my_r, (Real)my_c, (Real)my_g, (Real)my_o);
-            if (p.obs_self_v != nullptr)  // :137-139
-                store4<Real>(reinterpret_cast<Real *>(p.obs_self_v) + rec * 4, lut_row[my_r], lut_col[my_c],
-                             lut_cnt[my_g], lut_cnt[my_o]);
-            if (p.obs_others != nullptr) {  // :143-151
-                Real *oo = reinterpret_cast<Real *>(p.obs_others) + rec * L;
-                if (N == 1) {
-                    store2<Real>(oo, lut_row[my_r], lut_col[my_c]);
-                } else {
+            for (int d = 0; d < p.n_dst; ++d) {
+                const CkOut &o = p.out[d];
+                if (o.vec != nullptr)  // get_global_state, :89-93
+                    store4<Real>(reinterpret_cast<Real *>(o.vec) + rec * 4, (Real)my_r, (Real)my_c, (Real)my_g, (Real)my_o);
+                if (o.obs_self_v != nullptr)  // :137-139
+                    store4<Real>(reinterpret_cast<Real *>(o.obs_self_v) + rec * 4, lut_row[my_r], lut_col[my_c],
+                                 lut_cnt[my_g], lut_cnt[my_o]);
+                if (o.obs_others != nullptr) {  // :143-151
+                    Real *oo = reinterpret_cast<Real *>(o.obs_others) + rec * L;
+                    if (N == 1) {
+                        store2<Real>(oo, lut_row[my_r], lut_col[my_c]);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < N - 1; ++k) {
-                        const int j = k + (k >= a ? 1 : 0);
-                        store2<Real>(oo + 2 * k, lut_row[pick<N>(ar, j)], lut_col[pick<N>(ac, j)]);
+                        for (int k = 0; k < N - 1; ++k) {
+                            const int j = k + (k >= a ? 1 : 0);
+                            store2<Real>(oo + 2 * k, lut_row[pick<N>(ar, j)], lut_col[pick<N>(ac, j)]);
+                        }
                     }
                 }
             }
@@ -332,21 +358,23 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 done = (steps == p.max_steps) || (rem == 0ull);
             }
             if (valid) {
-                if (p.local_rewards != nullptr) {
-                    double mine = rew[0];
+                double mine = rew[0];
 #pragma unroll
-                    for (int i = 1; i < N; ++i) mine = (a == i) ? rew[i] : mine;
-                    reinterpret_cast<Real *>(p.local_rewards)[((size_t)t * B + env) * N + a] = (Real)mine;
-                }
-                if (a == 0) {
-                    if (p.reward != nullptr) reinterpret_cast<Real *>(p.reward)[(size_t)t * B + env] = (Real)total;
-                    if (p.done != nullptr) p.done[(size_t)t * B + env] = done ? 1 : 0;
+                for (int i = 1; i < N; ++i) mine = (a == i) ? rew[i] : mine;
+                const size_t orow = (size_t)t * OB + oe0 + env;
+                for (int d = 0; d < p.n_dst; ++d) {
+                    const CkOut &o = p.out[d];
+                    if (o.local_rewards != nullptr) reinterpret_cast<Real *>(o.local_rewards)[orow * N + a] = (Real)mine;
+                    if (a == 0) {
+                        if (o.reward != nullptr) reinterpret_cast<Real *>(o.reward)[orow] = (Real)total;
+                        if (o.done != nullptr) o.done[orow] = done ? 1 : 0;
+                    }
                 }
             }
             if (p.auto_reset && done) reset_state();
         }
         emit(t);
-        if (sel && a == 0 && p.done != nullptr) p.done[env] = 0;  // checkers.py:291
+        if (sel && a == 0 && o0.done != nullptr) o0.done[oe0 + env] = 0;  // checkers.py:291
     }
 
     // ---- store compact state
@@ -376,8 +404,7 @@ static int launch_ck(const CkParams &p, cudaStream_t stream) {
     }
     const int ntiles = (p.B + Gm::EW - 1) / Gm::EW;
     const int nblocks = (ntiles + kCkWarpsPerBlock - 1) / kCkWarpsPerBlock;
-    kern<<<nblocks, kCkWarpsPerBlock * kWarp, Gm::kSmemBytes, stream>>>(p);
-    CM3_CUDA(cudaGetLastError());
+    CM3_CUDA(launch_kernel(kern, nblocks, kCkWarpsPerBlock * kWarp, Gm::kSmemBytes, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 
@@ -408,6 +435,9 @@ static int dispatch_ck(int R, int C, int O, int N, const CkParams &p, cudaStream
     return CM3_ERR_UNSUPPORTED;
 }
 
+// This file is compiled twice (cm3_b200/build.py): -DCM3_CK_REAL=0 instantiates the float kernels,
+// -DCM3_CK_REAL=1 the double ones; the two objects build in parallel.
+#if CM3_CK_REAL == 0
 bool checkers_geometry_supported(int R, int C, int O, int N) {
     if (N < 1 || N > CM3_MAX_AGENTS) return false;
 #define X(r, c, o) \
@@ -417,9 +447,18 @@ bool checkers_geometry_supported(int R, int C, int O, int N) {
     return false;
 }
 
-int checkers_launch(int R, int C, int O, int N, int real, const CkParams &p, cudaStream_t stream) {
-    if (real == CM3_REAL_F64) return dispatch_ck<double>(R, C, O, N, p, stream);
+int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
     return dispatch_ck<float>(R, C, O, N, p, stream);
 }
+
+int checkers_launch(int R, int C, int O, int N, int real, const CkParams &p, cudaStream_t stream) {
+    if (real == CM3_REAL_F64) return checkers_launch_f64(R, C, O, N, p, stream);
+    return checkers_launch_f32(R, C, O, N, p, stream);
+}
+#else
+int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
+    return dispatch_ck<double>(R, C, O, N, p, stream);
+}
+#endif
 
 }  // namespace cm3

@@ -99,4 +99,29 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 __host__ __device__ constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Consecutive step launches on a stream depend on each other only through the compact state.
+// With the launch attribute below the next grid becomes resident (block scheduling, parameter
+// and LUT setup) while the previous grid drains its last stores, and blocks at pdl_wait() until
+// the previous grid has completed and its writes are visible.  Both instructions are no-ops for
+// a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename P>
+inline cudaError_t launch_kernel(void (*kern)(P), int nblocks, int nthreads, size_t smem, cudaStream_t stream,
+                                 bool pdl, const P &params) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblocks, 1, 1);
+    cfg.blockDim = dim3((unsigned)nthreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, params);
+}
+
 }  // namespace cm3

@@ -11,8 +11,19 @@ constexpr int kCkMaxTR = 16;   // n_rows + 2*n_obs
 constexpr int kCkMaxTC = 40;   // n_columns + 2*n_obs + 1
 constexpr int kCkMaxCnt = 34;  // n_rows*n_columns/2 + 1
 
+constexpr int kMaxDst = CM3_MAX_DST;  // destination buffer sets of a fused rollout + all-gather
+
 enum CkMode { kCkStep = 0, kCkReset = 1 };
 enum PtMode { kPtStep = 0, kPtReset = 1 };
+
+struct CkOut {
+    char *grid, *vec, *obs_others, *obs_self_t, *obs_self_v, *reward, *local_rewards;
+    uint8_t *done;
+};
+struct PtOut {
+    char *global_state, *obs_others, *obs_self, *reward, *reward_n;
+    uint8_t *done;
+};
 
 struct CkParams {
     uint64_t *remaining;
@@ -22,8 +33,12 @@ struct CkParams {
     const uint8_t *goal_idx;
     const uint8_t *env_mask;
     int8_t *actions_out;
-    char *grid, *vec, *obs_others, *obs_self_t, *obs_self_v, *reward, *local_rewards;
-    uint8_t *done;
+    // Output buffer sets.  out[0] is the only one for reset / step / rollout (out_B = B,
+    // out_env0 = 0); rollout_gather stores every element to all n_dst sets, each laid out
+    // [T][out_B][...] with this shard at env offset out_env0.  All sets have the same NULL fields.
+    CkOut out[kMaxDst];
+    int n_dst;
+    long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
     unsigned long long seed;
     long long t0, env_id_offset;
@@ -31,6 +46,13 @@ struct CkParams {
     // (r - total_rows/2.0)/total_rows etc., evaluated on the host in float64 exactly as
     // checkers.py:120-121,139 write them, so the device never divides
     double norm_row[kCkMaxTR], norm_col[kCkMaxTC], norm_cnt[kCkMaxCnt];
+};
+
+// World constants in the arithmetic type of the kernel.  far2: squared centre distance beyond
+// which the contact force is exactly +-0 in that arithmetic; near2: beyond which two agents cannot
+// be in collision (particle.cu).
+template <typename Real> struct PtConsts {
+    Real dt, keep, contact_force, contact_margin, dist_min, mass, sensitivity, neg_reach, far2, near2;
 };
 
 struct PtParams {
@@ -41,8 +63,9 @@ struct PtParams {
     int8_t *actions_out;
     const char *init_pos, *init_landmarks;
     const uint8_t *env_mask;
-    char *global_state, *obs_others, *obs_self, *reward, *reward_n;
-    uint8_t *done;
+    PtOut out[kMaxDst];  // see CkParams
+    int n_dst;
+    long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
     unsigned long long seed;
     long long t0, env_id_offset, reset_counter;
@@ -50,10 +73,15 @@ struct PtParams {
     double agents_x[CM3_MAX_AGENTS], agents_y[CM3_MAX_AGENTS];
     double landmarks_x[CM3_MAX_AGENTS], landmarks_y[CM3_MAX_AGENTS];
     double initial_std, prob_random;
+    PtConsts<float> kf;   // the constants above rounded to the kernel's Real on the host
+    PtConsts<double> kd;
 };
 
 bool checkers_geometry_supported(int R, int C, int O, int N);
 int checkers_launch(int R, int C, int O, int N, int real, const CkParams &p, cudaStream_t stream);
+int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
+int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);
+bool pdl_enabled();  // programmatic dependent launch between consecutive step launches (CM3_PDL=0 disables)
 
 }  // namespace cm3

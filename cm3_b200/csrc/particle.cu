@@ -40,6 +40,18 @@ template <> __device__ __forceinline__ void ld4<double>(const double *p, double 
     const double2 u = reinterpret_cast<const double2 *>(p)[0], v = reinterpret_cast<const double2 *>(p)[1];
     a = u.x; b = u.y; c = v.x; d = v.y;
 }
+template <typename Real> __device__ __forceinline__ void ld2(const Real *p, Real &a, Real &b);
+template <> __device__ __forceinline__ void ld2<float>(const float *p, float &a, float &b) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    a = v.x; b = v.y;
+}
+template <> __device__ __forceinline__ void ld2<double>(const double *p, double &a, double &b) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    a = v.x; b = v.y;
+}
+template <typename Real> __device__ __forceinline__ const PtConsts<Real> &pt_consts(const PtParams &p);
+template <> __device__ __forceinline__ const PtConsts<float> &pt_consts<float>(const PtParams &p) { return p.kf; }
+template <> __device__ __forceinline__ const PtConsts<double> &pt_consts<double>(const PtParams &p) { return p.kd; }
 template <typename Real> __device__ __forceinline__ void st4(Real *p, Real a, Real b, Real c, Real d);
 template <> __device__ __forceinline__ void st4<float>(float *p, float a, float b, float c, float d) {
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
@@ -47,13 +59,6 @@ template <> __device__ __forceinline__ void st4<float>(float *p, float a, float 
 template <> __device__ __forceinline__ void st4<double>(double *p, double a, double b, double c, double d) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
     reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
-}
-
-template <typename Real, int N> __device__ __forceinline__ Real pickr(const Real (&v)[N], int idx) {
-    Real r = v[0];
-#pragma unroll
-    for (int i = 1; i < N; ++i) r = (idx == i) ? v[i] : r;
-    return r;
 }
 
 // np.logaddexp(0, x) - NumPy's npy_logaddexp with x1 = 0 (core.py:192)
@@ -93,13 +98,57 @@ template <> struct Contact<double> {
 // precisions draw the same initial states
 __device__ __forceinline__ double u01_24(uint32_t w) { return (double)(w >> 8) * (1.0 / 16777216.0); }
 
+// reset_world() of one agent on Philox4x32-10 keyed by (seed; global env id, reset counter)
+// (multi-goal_spread.py:75-91).  Deliberately NOT inlined: resets are rare (once per episode) and
+// an inlined copy lets the compiler hoist ~300 instructions of Philox / Box-Muller arithmetic
+// above the step loop, where every thread of every launch pays for them.
+template <typename Real> struct ResetDraw { Real px, py, lx, ly; };
+
+template <typename Real>
+__device__ __noinline__ ResetDraw<Real> draw_reset(const PtParams &p, unsigned long long genv,
+                                                   unsigned long long counter, int a) {
+    using Op = RealOps<Real>;
+    ResetDraw<Real> d;
+    const uint32_t c0 = (uint32_t)genv, c1 = (uint32_t)(genv >> 32);
+    const uint32_t c2 = (uint32_t)counter, c3 = kTagReset | ((uint32_t)(counter >> 32) & 0xFFFFu);
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    bool randomise = false;
+    if (p.prob_random > 0.0) {  // rand_num, :75
+        const Philox4 wb = philox4x32_10(c0, c1 ^ 0xF0000000u, c2, c3, k0, k1);
+        randomise = u01_24(wb.x) < p.prob_random;
+    }
+    if (randomise) {  // :77-78, :88-89
+        const Philox4 wa = philox4x32_10(c0, c1 ^ ((uint32_t)(a + 1) << 24), c2, c3, k0, k1);
+        d.px = (Real)(-1.0 + 2.0 * u01_24(wa.x)); d.py = (Real)(-1.0 + 2.0 * u01_24(wa.y));
+        d.lx = (Real)(-1.0 + 2.0 * u01_24(wa.z)); d.ly = (Real)(-1.0 + 2.0 * u01_24(wa.w));
+    } else {  // :80-83, :91
+        Real nx = 0, ny = 0;
+        if (p.initial_std != 0.0) {  // Box-Muller on (0,1] x [0,1)
+            const Philox4 wa = philox4x32_10(c0, c1 ^ ((uint32_t)(a + 1) << 24), c2, c3, k0, k1);
+            const Real r0 = Op::sqrt(Op::mul((Real)-2, Op::log((Real)(u01_24(wa.x) + 1.0 / 16777216.0))));
+            const Real r1 = Op::sqrt(Op::mul((Real)-2, Op::log((Real)(u01_24(wa.z) + 1.0 / 16777216.0))));
+            Real s0, c0f, s1, c1f;
+            Op::sincospi((Real)(2.0 * u01_24(wa.y)), &s0, &c0f);
+            Op::sincospi((Real)(2.0 * u01_24(wa.w)), &s1, &c1f);
+            nx = Op::mul(Op::mul(r0, c0f), (Real)p.initial_std);
+            ny = Op::mul(Op::mul(r1, c1f), (Real)p.initial_std);
+        }
+        d.px = Op::add((Real)p.agents_x[a], nx); d.py = Op::add((Real)p.agents_y[a], ny);
+        d.lx = (Real)p.landmarks_x[a]; d.ly = (Real)p.landmarks_y[a];
+    }
+    return d;
+}
+
 template <int N, typename Real>
 __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_constant__ PtParams p) {
     using Op = RealOps<Real>;
     constexpr int NP = (N == 3) ? 4 : N;
     constexpr int EW = kWarp / NP;
-    constexpr int LO = 4 * (N > 1 ? N - 1 : 1);
+    constexpr int NO = (N > 1) ? N - 1 : 1;  // "other" agents per agent
+    constexpr int LO = 4 * NO;
     constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+    pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * kPtThreads + threadIdx.x) >> 5;
@@ -111,9 +160,20 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     const bool valid = (a < N) && (env < p.B);
     const size_t B = (size_t)p.B;
 
-    const Real dt = (Real)p.dt, keep = (Real)(1.0 - p.damping), cf = (Real)p.contact_force;
-    const Real km = (Real)p.contact_margin, dist_min = (Real)p.dist_min, mass = (Real)p.mass;
-    const Real sens = (Real)p.sensitivity, neg_reach = (Real)(-p.reach_thresh);
+    // world constants, rounded to Real once on the host (no per-thread F2F conversions)
+    const PtConsts<Real> &K = pt_consts<Real>(p);
+    const Real dt = K.dt, keep = K.keep, cf = K.contact_force, km = K.contact_margin, dist_min = K.dist_min;
+    const Real mass = K.mass, sens = K.sensitivity, neg_reach = K.neg_reach;
+    // squared distances beyond which a pair provably contributes exactly nothing (see below)
+    const Real far2 = K.far2, near2 = K.near2;
+    const bool unit_mass = (mass == (Real)1);  // x / 1 == x exactly: skip the IEEE division
+
+    // lane of the k-th "other" agent of my env, in index order (multi-goal_spread.py:149-152)
+    int src[NO];
+#pragma unroll
+    for (int k = 0; k < NO; ++k) src[k] = (N > 1) ? gb + k + (k >= a ? 1 : 0) : lane;
+
+    pdl_wait();  // state written by the previous launch is visible from here on
 
     // ---- state
     Real vx = 0, vy = 0, px = (Real)(2 * lane), py = 0, lx = 0, ly = 0;  // idle lanes stay apart
@@ -121,8 +181,7 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     uint32_t reached = 0;
     if (valid) {
         ld4<Real>(reinterpret_cast<const Real *>(p.sv) + ((size_t)env * N + a) * 4, vx, vy, px, py);
-        const Real *lm = reinterpret_cast<const Real *>(p.landmarks) + ((size_t)env * N + a) * 2;
-        lx = lm[0]; ly = lm[1];
+        ld2<Real>(reinterpret_cast<const Real *>(p.landmarks) + ((size_t)env * N + a) * 2, lx, ly);
         steps = p.steps[env];
         collisions = p.collisions[env];
         reached = p.reached[env];
@@ -135,58 +194,45 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             const Real *il = reinterpret_cast<const Real *>(p.init_landmarks) + ((size_t)env * N + a) * 2;
             px = ip[0]; py = ip[1]; lx = il[0]; ly = il[1];
         } else {
-            const unsigned long long genv = (unsigned long long)(p.env_id_offset + env);
-            const uint32_t c0 = (uint32_t)genv, c1 = (uint32_t)(genv >> 32);
-            const uint32_t c2 = (uint32_t)counter, c3 = kTagReset | ((uint32_t)(counter >> 32) & 0xFFFFu);
-            const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-            const Philox4 wb = philox4x32_10(c0, c1 ^ 0xF0000000u, c2, c3, k0, k1);  // rand_num, :75
-            const Philox4 wa = philox4x32_10(c0, c1 ^ ((uint32_t)(a + 1) << 24), c2, c3, k0, k1);
-            if (u01_24(wb.x) < p.prob_random) {  // :77-78, :88-89
-                px = (Real)(-1.0 + 2.0 * u01_24(wa.x)); py = (Real)(-1.0 + 2.0 * u01_24(wa.y));
-                lx = (Real)(-1.0 + 2.0 * u01_24(wa.z)); ly = (Real)(-1.0 + 2.0 * u01_24(wa.w));
-            } else {  // :80-83, :91
-                Real nx = 0, ny = 0;
-                if (p.initial_std != 0.0) {  // Box-Muller on (0,1] x [0,1)
-                    const Real r0 = Op::sqrt(Op::mul((Real)-2, Op::log((Real)(u01_24(wa.x) + 1.0 / 16777216.0))));
-                    const Real r1 = Op::sqrt(Op::mul((Real)-2, Op::log((Real)(u01_24(wa.z) + 1.0 / 16777216.0))));
-                    Real s0, c0f, s1, c1f;
-                    Op::sincospi((Real)(2.0 * u01_24(wa.y)), &s0, &c0f);
-                    Op::sincospi((Real)(2.0 * u01_24(wa.w)), &s1, &c1f);
-                    nx = Op::mul(Op::mul(r0, c0f), (Real)p.initial_std);
-                    ny = Op::mul(Op::mul(r1, c1f), (Real)p.initial_std);
-                }
-                const int ai = a < N ? a : 0;
-                px = Op::add((Real)p.agents_x[ai], nx); py = Op::add((Real)p.agents_y[ai], ny);
-                lx = (Real)p.landmarks_x[ai]; ly = (Real)p.landmarks_y[ai];
-            }
+            const ResetDraw<Real> d = draw_reset<Real>(p, (unsigned long long)(p.env_id_offset + env), counter,
+                                                       a < N ? a : 0);
+            px = d.px; py = d.py; lx = d.lx; ly = d.ly;
         }
         vx = 0; vy = 0; steps = 0; collisions = 0; reached = 0;  // :84-86, :93; environment.py:148
     };
 
-    // observations of the current state -> outputs of slot t (multi-goal_spread.py:145-154,
-    // environment.py:113-116)
-    auto emit = [&](int t) {
-        Real avx[N], avy[N], apx[N], apy[N];
+    // (vel, pos) of the other agents of my env, straight from their lanes
+    Real ovx[NO], ovy[NO], opx[NO], opy[NO];
+    auto gather_others = [&]() {
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            avx[j] = __shfl_sync(kFullMask, vx, gb + j); avy[j] = __shfl_sync(kFullMask, vy, gb + j);
-            apx[j] = __shfl_sync(kFullMask, px, gb + j); apy[j] = __shfl_sync(kFullMask, py, gb + j);
+        for (int k = 0; k < NO; ++k) {
+            ovx[k] = __shfl_sync(kFullMask, vx, src[k]); ovy[k] = __shfl_sync(kFullMask, vy, src[k]);
+            opx[k] = __shfl_sync(kFullMask, px, src[k]); opy[k] = __shfl_sync(kFullMask, py, src[k]);
         }
+    };
+
+    // observations of the current state -> outputs of slot t (multi-goal_spread.py:145-154,
+    // environment.py:113-116); needs gather_others() of the current state
+    const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
+    auto emit = [&](int t) {
         if (!valid) return;
-        const size_t rec = ((size_t)t * B + env) * N + a;
-        if (p.global_state != nullptr) st4<Real>(reinterpret_cast<Real *>(p.global_state) + rec * 4, vx, vy, px, py);
-        if (p.obs_self != nullptr) st4<Real>(reinterpret_cast<Real *>(p.obs_self) + rec * 4, vx, vy, px, py);
-        if (p.obs_others != nullptr) {
-            Real *oo = reinterpret_cast<Real *>(p.obs_others) + rec * LO;
-            if (N == 1) {
-                st4<Real>(oo, Op::sub(vx, vx), Op::sub(vy, vy), Op::sub(px, px), Op::sub(py, py));
-            } else {
+        const size_t rec = ((size_t)t * OB + oe0 + env) * N + a;
+        Real dvx[NO], dvy[NO], dpx[NO], dpy[NO];
 #pragma unroll
-                for (int k = 0; k < N - 1; ++k) {
-                    const int j = k + (k >= a ? 1 : 0);
-                    st4<Real>(oo + 4 * k, Op::sub(pickr<Real, N>(avx, j), vx), Op::sub(pickr<Real, N>(avy, j), vy),
-                              Op::sub(pickr<Real, N>(apx, j), px), Op::sub(pickr<Real, N>(apy, j), py));
-                }
+        for (int k = 0; k < NO; ++k) {  // N == 1: "others" is the agent itself, :148-153
+            dvx[k] = Op::sub(ovx[k], vx); dvy[k] = Op::sub(ovy[k], vy);
+            dpx[k] = Op::sub(opx[k], px); dpy[k] = Op::sub(opy[k], py);
+        }
+        // n_dst > 1 (rollout_gather): the same records go to the rollout buffers of every GPU of
+        // the node - peer memory over NVLink
+        for (int d = 0; d < p.n_dst; ++d) {
+            const PtOut &o = p.out[d];
+            if (o.global_state != nullptr) st4<Real>(reinterpret_cast<Real *>(o.global_state) + rec * 4, vx, vy, px, py);
+            if (o.obs_self != nullptr) st4<Real>(reinterpret_cast<Real *>(o.obs_self) + rec * 4, vx, vy, px, py);
+            if (o.obs_others != nullptr) {
+                Real *oo = reinterpret_cast<Real *>(o.obs_others) + rec * LO;
+#pragma unroll
+                for (int k = 0; k < NO; ++k) st4<Real>(oo + 4 * k, dvx[k], dvy[k], dpx[k], dpy[k]);
             }
         }
     };
@@ -197,6 +243,7 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         if (p.mode == kPtReset) {
             sel = valid && (p.env_mask == nullptr || p.env_mask[env] != 0);
             if (sel) reset_state((unsigned long long)p.reset_counter);
+            gather_others();
         } else {
             // ---- action -> control force (environment.py:194-214, core.py:134-140)
             int act = 0;
@@ -211,30 +258,34 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             Real fy = (act == 3) ? (Real)-1 : (act == 4) ? (Real)1 : (Real)0;
             fx = Op::mul(fx, sens); fy = Op::mul(fy, sens);
 
-            // ---- contact forces, other agents in index order (core.py:143-155, 180-196)
+            // ---- contact forces, other agents in index order (core.py:143-155, 180-196).
+            // The reference evaluates the softplus penetration for EVERY pair at every distance;
+            // beyond dist_min + ~110 k (float) / ~760 k (double) exp() underflows to exactly 0, so
+            // pen == 0, the force is +-0 and "F + p_force" returns p_force bit for bit (p_force is
+            // never -0: it starts as +0 or +-sensitivity).  Those pairs are skipped: same bits,
+            // none of the double-precision sqrt / div / exp / log1p instructions.
             if (N > 1) {
-                Real opx[N], opy[N];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    opx[j] = __shfl_sync(kFullMask, px, gb + j);
-                    opy[j] = __shfl_sync(kFullMask, py, gb + j);
-                }
-#pragma unroll
-                for (int k = 0; k < N - 1; ++k) {
-                    const int j = k + (k >= a ? 1 : 0);
-                    Real dx, dy, dist, x;
-                    Contact<Real>::eval(px, py, pickr<Real, N>(opx, j), pickr<Real, N>(opy, j), p.dist_min,
-                                        p.contact_margin, dx, dy, dist, x);
-                    const Real pen = Op::mul(logaddexp0<Real>(x), km);
-                    fx = Op::add(Op::mul(Op::div(Op::mul(cf, dx), dist), pen), fx);
-                    fy = Op::add(Op::mul(Op::div(Op::mul(cf, dy), dist), pen), fy);
+                for (int k = 0; k < NO; ++k) {
+                    const Real qx = __shfl_sync(kFullMask, px, src[k]), qy = __shfl_sync(kFullMask, py, src[k]);
+                    const Real ex = Op::sub(px, qx), ey = Op::sub(py, qy);
+                    const Real d2 = Op::add(Op::mul(ex, ex), Op::mul(ey, ey));
+                    if (!(d2 > far2)) {  // near, coincident or NaN: the literal evaluation
+                        Real dx, dy, dist, x;
+                        Contact<Real>::eval(px, py, qx, qy, p.dist_min, p.contact_margin, dx, dy, dist, x);
+                        const Real pen = Op::mul(logaddexp0<Real>(x), km);
+                        fx = Op::add(Op::mul(Op::div(Op::mul(cf, dx), dist), pen), fx);
+                        fy = Op::add(Op::mul(Op::div(Op::mul(cf, dy), dist), pen), fy);
+                    }
                 }
             }
             // ---- integrate (core.py:158-169)
             vx = Op::mul(vx, keep); vy = Op::mul(vy, keep);
-            vx = Op::add(vx, Op::mul(Op::div(fx, mass), dt)); vy = Op::add(vy, Op::mul(Op::div(fy, mass), dt));
+            if (!unit_mass) { fx = Op::div(fx, mass); fy = Op::div(fy, mass); }
+            vx = Op::add(vx, Op::mul(fx, dt)); vy = Op::add(vy, Op::mul(fy, dt));
             px = Op::add(px, Op::mul(vx, dt)); py = Op::add(py, Op::mul(vy, dt));
             steps += 1;  // environment.py:93
+            gather_others();
 
             // ---- reward (multi-goal_spread.py:121-138)
             const Real tx = Op::sub(px, lx), ty = Op::sub(py, ly);
@@ -242,51 +293,55 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             const bool my_reached = rew >= neg_reach;
             int hits = 0;
             if (N > 1) {
-                Real npx[N], npy[N];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    npx[j] = __shfl_sync(kFullMask, px, gb + j);
-                    npy[j] = __shfl_sync(kFullMask, py, gb + j);
-                }
-#pragma unroll
-                for (int k = 0; k < N - 1; ++k) {
-                    const int j = k + (k >= a ? 1 : 0);
-                    const Real dx = Op::sub(pickr<Real, N>(npx, j), px), dy = Op::sub(pickr<Real, N>(npy, j), py);
-                    const Real dist = Op::sqrt(Op::add(Op::mul(dx, dx), Op::mul(dy, dy)));
-                    if (dist < dist_min) { rew = Op::sub(rew, (Real)1); hits += 1; }
+                for (int k = 0; k < NO; ++k) {
+                    const Real dx = Op::sub(opx[k], px), dy = Op::sub(opy[k], py);
+                    const Real d2 = Op::add(Op::mul(dx, dx), Op::mul(dy, dy));
+                    // sqrt is monotonic: d2 > near2 = (1.01 dist_min)^2 cannot round below dist_min
+                    if (!(d2 > near2)) {
+                        if (Op::sqrt(d2) < dist_min) { rew = Op::sub(rew, (Real)1); hits += 1; }
+                    }
                 }
             }
             // ---- env-level reductions over the NP lanes of my env
             Real total = 0;
             int all_hits = 0;
-            uint32_t reach_bits = 0;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const Real rj = __shfl_sync(kFullMask, rew, gb + j);
                 total = (j == 0) ? rj : Op::add(total, rj);  // np.sum, environment.py:107
-                all_hits += __shfl_sync(kFullMask, hits, gb + j);
-                reach_bits |= (__shfl_sync(kFullMask, (int)my_reached, gb + j) ? 1u : 0u) << j;
+                if (N > 1) all_hits += __shfl_sync(kFullMask, hits, gb + j);
             }
+            const uint32_t reach_bits = (__ballot_sync(kFullMask, my_reached) >> gb) & ((1u << N) - 1u);
             collisions += all_hits;
             reached = reach_bits;
             const bool done = (steps == p.max_steps) || (reach_bits == (1u << N) - 1u);  // environment.py:118
             if (valid) {
-                if (p.reward_n != nullptr) reinterpret_cast<Real *>(p.reward_n)[((size_t)t * B + env) * N + a] = rew;
-                if (a == 0) {
-                    if (p.reward != nullptr) reinterpret_cast<Real *>(p.reward)[(size_t)t * B + env] = total;
-                    if (p.done != nullptr) p.done[(size_t)t * B + env] = done ? 1 : 0;
+                const size_t orow = (size_t)t * OB + oe0 + env;
+                for (int d = 0; d < p.n_dst; ++d) {
+                    const PtOut &o = p.out[d];
+                    if (o.reward_n != nullptr) reinterpret_cast<Real *>(o.reward_n)[orow * N + a] = rew;
+                    if (a == 0) {
+                        if (o.reward != nullptr) reinterpret_cast<Real *>(o.reward)[orow] = total;
+                        if (o.done != nullptr) o.done[orow] = done ? 1 : 0;
+                    }
                 }
             }
-            if (p.auto_reset && done) reset_state((unsigned long long)(p.t0 + t + 1));
+            if (p.auto_reset) {
+                if (done) reset_state((unsigned long long)(p.t0 + t + 1));
+                if (__any_sync(kFullMask, done)) gather_others();
+            }
         }
         emit(t);
-        if (sel && a == 0 && p.done != nullptr) p.done[env] = 0;  // np.any(done_n), environment.py:149
+        if (sel && a == 0 && p.out[0].done != nullptr) p.out[0].done[oe0 + env] = 0;  // np.any(done_n), environment.py:149
     }
 
     if (valid) {
         st4<Real>(reinterpret_cast<Real *>(p.sv) + ((size_t)env * N + a) * 4, vx, vy, px, py);
-        Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + a) * 2;
-        lm[0] = lx; lm[1] = ly;
+        if (p.mode == kPtReset || p.auto_reset) {  // landmarks only change on a reset
+            Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + a) * 2;
+            lm[0] = lx; lm[1] = ly;
+        }
         if (a == 0) {
             p.steps[env] = steps;
             p.collisions[env] = collisions;
@@ -301,8 +356,7 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
     constexpr int EW = kWarp / NP;
     const int nwarps = (p.B + EW - 1) / EW;
     const int nblocks = (nwarps + kPtThreads / kWarp - 1) / (kPtThreads / kWarp);
-    particle_kernel<N, Real><<<nblocks, kPtThreads, 0, stream>>>(p);
-    CM3_CUDA(cudaGetLastError());
+    CM3_CUDA(launch_kernel(particle_kernel<N, Real>, nblocks, kPtThreads, 0, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 

@@ -38,6 +38,7 @@ extern "C" {
 
 #define CM3_ABI_VERSION 1
 #define CM3_MAX_AGENTS 4
+#define CM3_MAX_DST 8 /* destination buffer sets of *_rollout_gather (GPUs of one NVSwitch node) */
 
 typedef enum {
     CM3_OK = 0,
@@ -127,6 +128,23 @@ int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const i
                          uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
                          int8_t *actions_out, const cm3_checkers_outputs *outs, void *stream);
 
+/* Fused rollout + all-gather.  Same computation as cm3_checkers_rollout, but every output element
+ * is stored to n_dst destination buffer sets instead of one.  Each set is laid out
+ * [T][dst_B][...] per field and this handle's B envs occupy rows [dst_env0, dst_env0 + B).
+ * With dsts[] = the rollout buffers of all ranks of a node (peer device pointers obtained through
+ * CUDA IPC / symmetric memory; NVLink 5 + NVSwitch gives every GPU a direct store path to every
+ * peer) and dst_env0 = this rank's first global env id, the gathered [T][total_envs][...] batch
+ * materialises on every GPU straight from the step kernel's stores: the observation tile is
+ * expanded once in shared memory and leaves the SM as n_dst TMA bulk stores, with no staging pass
+ * through local HBM and no separate collective.  The reference has no counterpart (one env per
+ * process, alg/train_multiprocess.py:31-43); it stands where a data-parallel learner would
+ * all-gather its workers' rollouts.  All sets must have the same NULL fields.  Making the stores
+ * visible to the peers (a barrier after the stream work) is the caller's job. */
+int cm3_checkers_rollout_gather(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                                uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
+                                int8_t *actions_out, int32_t n_dst, const cm3_checkers_outputs *dsts,
+                                int64_t dst_B, int64_t dst_env0, void *stream);
+
 /* Host-buffer form of step: copies actions_host -> actions_dev, steps, copies every
  * non-NULL field of outs_host back from the matching field of outs_dev and waits for the
  * stream.  This is the call a host-side binding uses when its buffers live in host memory
@@ -211,6 +229,12 @@ int cm3_particle_step(cm3_particle_t h, const cm3_particle_state *st, const int8
 int cm3_particle_rollout(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
                          uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
                          int8_t *actions_out, const cm3_particle_outputs *outs, void *stream);
+
+/* Fused rollout + all-gather; see cm3_checkers_rollout_gather. */
+int cm3_particle_rollout_gather(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                                uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
+                                int8_t *actions_out, int32_t n_dst, const cm3_particle_outputs *dsts,
+                                int64_t dst_B, int64_t dst_env0, void *stream);
 
 int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st,
                            const int8_t *actions_host, int8_t *actions_dev,
