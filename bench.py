@@ -221,6 +221,28 @@ def bytes_per_env_step(env):
     return env.bytes_per_env_step()
 
 
+class GatherRunner(object):
+    """BASELINE.json configs[3]: every launch is one fused T-step rollout of this rank's shard
+    (device Philox actions, in-kernel episode reset) whose outputs are delivered to EVERY GPU as
+    [T, total_envs, ...] - by ncclAllGather ("nccl") or by the kernel's own peer stores over
+    NVLink ("peer", cm3_*_rollout_gather).  One "step" is still one env step of the whole batch."""
+
+    def __init__(self, env, shard, T, mode):
+        from cm3_b200.sharding import RolloutAllGather
+        self.env, self.T = env, T
+        self.g = RolloutAllGather(env, T, shard=shard, mode=mode)
+        self.mode = self.g.mode
+        self.launches = 0
+
+    def capture(self):
+        pass
+
+    def run(self, k):
+        for i in range(k // self.T):
+            self.g.rollout(seed=SEED, t0=self.launches * self.T, auto_reset=True, time_major=False)
+            self.launches += 1
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -238,7 +260,16 @@ def run_gpu(args):
     bpe = bytes_per_env_step(env)
     # ring larger than L2 (126 MB): at least 33 slots and >= 512 MB of outputs
     ring = max(MAX_STEPS, int(np.ceil(512e6 / (bpe * B))))
-    runner = StepRunner(env, spec, ring, SEED + rank)
+    gather_mode = None
+    if args.gather != "none":
+        from cm3_b200.sharding import EnvShard
+        T = MAX_STEPS
+        K = max(T, K // T * T)
+        W = max(T, (max(W, 3) + T - 1) // T * T)
+        runner = GatherRunner(env, EnvShard(world * B, rank=rank, world=world, local_rank=local_rank), T, args.gather)
+        gather_mode = runner.mode
+    else:
+        runner = StepRunner(env, spec, ring, SEED + rank)
     runner.capture()
 
     def barrier():
@@ -288,7 +319,28 @@ def run_gpu(args):
         "gpu_launches": K,
         "clocks": clocks,
     }
-    if rank == 0 and not args.no_extras:
+    if gather_mode is not None:
+        T = MAX_STEPS
+        el = 8 if env.dtype == torch.float64 else 4
+        out_b = sum(int(np.prod(sh[1:])) for k, sh in env.field_shapes().items() if k != "done") * el + 1
+        sent = out_b * B * (world - 1)  # bytes this GPU delivers to its peers per env step
+        out["gpu_launches"] = K // T
+        out["config"].update({"launch": "1 launch per %d fused env steps, device Philox actions" % T,
+                              "actions": "Philox4x32-10 on the device, keyed by (seed, global env id, step)",
+                              "rollout_all_gather": gather_mode,
+                              "l2": "gathered rollout buffer [%d][%d envs] = %.0f MB per GPU (> 126 MB L2 when >= 2 GPUs at the default size)" % (T, world * B, out_b * world * B * T / 1e6)})
+        out["roofline"].update({"kernel": "fused rollout + all-gather (%s)" % gather_mode,
+                                "algorithmic_bytes_per_env_step": out_b + (bpe - out_b - spec["n"]) / T,
+                                "nvlink_bytes_sent_per_gpu_per_step": sent,
+                                "nvlink_gbs_per_gpu": sent / (launch_us * 1e-6) / 1e9 if world > 1 else 0.0,
+                                "note": "bound by NVLink egress (900 GB/s per direction per GPU) once world > 1, not by HBM"})
+        a2 = (out_b + (bpe - out_b - spec["n"]) / T) * (world if gather_mode else 1) * B / (launch_us * 1e-6) / 1e9
+        out["roofline"]["achieved"] = a2  # HBM bytes written on THIS GPU: the whole gathered batch
+        out["roofline"]["frac"] = a2 / peak
+        out["roofline"]["bytes_per_launch"] = (out_b + (bpe - out_b - spec["n"]) / T) * world * B * T
+    if args.gather != "none":
+        pass  # the collective run reports the kernel-side number only
+    elif rank == 0 and not args.no_extras:
         out["e2e"] = measure_e2e(env, spec, args)
         out["extra"] = measure_extras(env, spec, args, peak)
         if world == 1:
@@ -421,6 +473,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--gather", default="none", choices=["none", "nccl", "peer", "auto"],
+                    help="all-gather the rollout buffers to every GPU (BASELINE.json configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,86 +1,82 @@
-"""Host-side mirrors of the reference's entity classes (multiagent/core.py:4-114).  They carry
-attributes only - the physics (World.step, core.py:117-196) runs in the CUDA kernel."""
-import numpy as np
+"""Host-side attribute records standing in for the reference's entity classes
+(multiagent/core.py:4-114).  The trainers and the scenario only read and write attributes on these
+objects (`env.world.landmarks[i].state.p_pos`, `agent.size`, `world.dt`, ...); all physics
+(World.step, core.py:117-196) runs in the CUDA step kernel, so nothing here computes.
+
+The attribute names and default values are the reference's; they are kept in tables so that the
+whole surface is visible at a glance.
+"""
+
+# name -> default, per record kind (reference line in the comment)
+_STATE_FIELDS = {"p_pos": None, "p_vel": None}                       # core.py:4-10
+_AGENT_STATE_FIELDS = dict(_STATE_FIELDS, c=None)                     # core.py:13-17
+_ACTION_FIELDS = {"u": None, "c": None}                               # core.py:20-25
+_ENTITY_FIELDS = {"name": "", "size": 0.050, "movable": False, "collide": True, "density": 25.0,
+                  "color": None, "max_speed": None, "accel": None, "initial_mass": 1.0}  # core.py:28-47
+_AGENT_EXTRA = {"movable": True, "silent": False, "blind": False, "u_noise": None, "c_noise": None,
+                "u_range": 1.0, "action_callback": None}              # core.py:60-79
+_WORLD_FIELDS = {"dim_c": 0, "dim_p": 2, "dim_color": 3,
+                 "dt": 0.1, "damping": 0.25, "contact_force": 1e+2, "contact_margin": 1e-3}  # core.py:86-99
 
 
-class EntityState(object):
+class _Record(object):
+    """A bag of attributes initialised from a table."""
+    _defaults = {}
+
     def __init__(self):
-        self.p_pos = None
-        self.p_vel = None
+        for key, value in self._defaults.items():
+            setattr(self, key, value)
+
+    def __repr__(self):
+        return "%s(%s)" % (type(self).__name__, ", ".join("%s=%r" % kv for kv in sorted(vars(self).items())))
 
 
-class AgentState(EntityState):
+class EntityState(_Record):
+    _defaults = _STATE_FIELDS
+
+
+class AgentState(_Record):
+    _defaults = _AGENT_STATE_FIELDS
+
+
+class Action(_Record):
+    _defaults = _ACTION_FIELDS
+
+
+class Entity(_Record):
+    _defaults = _ENTITY_FIELDS
+    _state_cls = EntityState
+
     def __init__(self):
-        super(AgentState, self).__init__()
-        self.c = None
+        _Record.__init__(self)
+        self.state = self._state_cls()
 
-
-class Action(object):
-    def __init__(self):
-        self.u = None
-        self.c = None
-
-
-class Entity(object):
-    def __init__(self):
-        self.name = ''
-        self.size = 0.050
-        self.movable = False
-        self.collide = True
-        self.density = 25.0
-        self.color = None
-        self.max_speed = None
-        self.accel = None
-        self.state = EntityState()
-        self.initial_mass = 1.0
-
-    @property
-    def mass(self):
-        return self.initial_mass
+    mass = property(lambda self: self.initial_mass)   # core.py:49-51
 
 
 class Landmark(Entity):
-    def __init__(self):
-        super(Landmark, self).__init__()
+    pass
 
 
 class Agent(Entity):
+    _defaults = dict(_ENTITY_FIELDS, **_AGENT_EXTRA)
+    _state_cls = AgentState
+
     def __init__(self):
-        super(Agent, self).__init__()
-        self.movable = True
-        self.silent = False
-        self.blind = False
-        self.u_noise = None
-        self.c_noise = None
-        self.u_range = 1.0
-        self.state = AgentState()
+        Entity.__init__(self)
         self.action = Action()
-        self.action_callback = None
 
 
-class World(object):
+class World(_Record):
+    _defaults = _WORLD_FIELDS
+
     def __init__(self):
-        self.agents = []
-        self.landmarks = []
-        self.dim_c = 0
-        self.dim_p = 2
-        self.dim_color = 3
-        self.dt = 0.1              # core.py:94
-        self.damping = 0.25        # core.py:96
-        self.contact_force = 1e+2  # core.py:98
-        self.contact_margin = 1e-3  # core.py:99
+        _Record.__init__(self)
+        self.agents, self.landmarks = [], []
 
-    @property
-    def entities(self):
-        return self.agents + self.landmarks
-
-    @property
-    def policy_agents(self):
-        return [agent for agent in self.agents if agent.action_callback is None]
-
-    @property
-    def scripted_agents(self):
-        return [agent for agent in self.agents if agent.action_callback is not None]
+    entities = property(lambda self: self.agents + self.landmarks)                               # core.py:102-104
+    policy_agents = property(lambda self: [a for a in self.agents if a.action_callback is None])  # core.py:107-109
+    scripted_agents = property(lambda self: [a for a in self.agents if a.action_callback is not None])
 
     def step(self):
         raise NotImplementedError("World.step is fused into the CUDA step kernel; call "

@@ -22,63 +22,58 @@ colors = np.array([[221, 127, 106], [204, 169, 120], [191, 196, 139], [176, 209,
 
 
 class Scenario(BaseScenario):
+    AGENT_SIZE = 0.15   # multi-goal_spread.py:47
+
     def make_world(self, n_agents, config, prob_random):
-        """multi-goal_spread.py:19-63"""
-        world = World()
-        world.dim_c = 0
-        self.n_agents = n_agents
-        self.agents_x = config['agents_x']
-        self.agents_y = config['agents_y']
-        self.landmarks_x = config['landmarks_x']
-        self.landmarks_y = config['landmarks_y']
-        self.initial_std = config['initial_std']
-        self.prob_random = prob_random
+        """multi-goal_spread.py:19-63: N agents (collide, silent, size 0.15), N static landmarks
+        that do not collide, preset positions from `config`, and one initial reset_world()."""
+        self.n_agents, self.prob_random = n_agents, prob_random
         self.config = dict(config)
-        world.collaborative = False
-        world.agents = [Agent() for i in range(n_agents)]
-        for i, agent in enumerate(world.agents):
-            agent.name = 'agent %d' % i
-            agent.idx = i
-            agent.collide = True
-            agent.silent = True
-            agent.size = 0.15
-            agent.reached = False
-        world.landmarks = [Landmark() for i in range(n_agents)]
-        for i, landmark in enumerate(world.landmarks):
-            landmark.name = 'landmark %d' % i
-            landmark.idx = i
-            landmark.collide = False
-            landmark.movable = False
-        self.colors = colors
-        self.collisions = 0
-        self._env = None          # set by MultiAgentEnv: the device-backed stepper
+        for key in ("agents_x", "agents_y", "landmarks_x", "landmarks_y", "initial_std"):
+            setattr(self, key, config[key])
+        self.colors, self.collisions = colors, 0
+        self._env = None                      # set by MultiAgentEnv: the device-backed stepper
+
+        world = World()
+        world.dim_c, world.collaborative = 0, False
         world._cm3_scenario = self
+        for idx in range(n_agents):
+            agent, landmark = Agent(), Landmark()
+            agent.name, landmark.name = "agent %d" % idx, "landmark %d" % idx
+            agent.idx = landmark.idx = idx
+            agent.collide, agent.silent, agent.size, agent.reached = True, True, self.AGENT_SIZE, False
+            landmark.collide, landmark.movable = False, False
+            world.agents.append(agent)
+            world.landmarks.append(landmark)
         self.reset_world(world)
         return world
 
+    def _draw_initial_positions(self, dim_p):
+        """The host RNG draws of multi-goal_spread.py:75-91, in the reference's order: one
+        random.random(); then either uniform(-1, 1, 2) per agent followed by the same per landmark,
+        or two scalar normal(0, initial_std) per agent (x, then y - drawn even when std == 0) with
+        the landmarks on their presets.  Returns (agent_pos [N,2], landmark_pos [N,2])."""
+        n = self.n_agents
+        if random.random() < self.prob_random:
+            agent_pos = np.stack([np.random.uniform(-1, +1, dim_p) for _ in range(n)])
+            landmark_pos = np.stack([np.random.uniform(-1, +1, dim_p) for _ in range(n)])
+        else:
+            jitter = np.array([[np.random.normal(0, self.initial_std), np.random.normal(0, self.initial_std)]
+                               for _ in range(n)])
+            agent_pos = np.stack([self.agents_x[:n], self.agents_y[:n]], axis=1) + jitter
+            landmark_pos = np.stack([self.landmarks_x[:n], self.landmarks_y[:n]], axis=1).astype(float)
+        return agent_pos, landmark_pos
+
     def reset_world(self, world):
-        """multi-goal_spread.py:65-93 - same draws, same order, same global RNGs."""
-        for i, agent in enumerate(world.agents):
-            agent.color = self.colors[i] / 256
-        for i, landmark in enumerate(world.landmarks):
-            landmark.color = self.colors[i] / 256
-        rand_num = random.random()
-        for i, agent in enumerate(world.agents):
-            if rand_num < self.prob_random:
-                agent.state.p_pos = np.random.uniform(-1, +1, world.dim_p)
-            else:
-                x = self.agents_x[i] + np.random.normal(0, self.initial_std)
-                y = self.agents_y[i] + np.random.normal(0, self.initial_std)
-                agent.state.p_pos = np.array([x, y])
-            agent.state.p_vel = np.zeros(world.dim_p)
+        """multi-goal_spread.py:65-93 - same draws, same order, same global RNG streams, so a
+        trainer that seeds `random` and `np.random` sees the reference's episodes."""
+        agent_pos, landmark_pos = self._draw_initial_positions(world.dim_p)
+        for i, (agent, landmark) in enumerate(zip(world.agents, world.landmarks)):
+            agent.color = landmark.color = self.colors[i] / 256
+            agent.state.p_pos, landmark.state.p_pos = agent_pos[i].copy(), landmark_pos[i].copy()
+            agent.state.p_vel, landmark.state.p_vel = np.zeros(world.dim_p), np.zeros(world.dim_p)
             agent.state.c = np.zeros(world.dim_c)
             agent.reached = False
-        for i, landmark in enumerate(world.landmarks):
-            if rand_num < self.prob_random:
-                landmark.state.p_pos = np.random.uniform(-1, +1, world.dim_p)
-            else:
-                landmark.state.p_pos = np.array([self.landmarks_x[i], self.landmarks_y[i]])
-            landmark.state.p_vel = np.zeros(world.dim_p)
         self.collisions = 0
         if self._env is not None:
             self._env._world_was_reset()
@@ -113,26 +108,23 @@ class Scenario(BaseScenario):
 
     def is_collision(self, agent1, agent2):
         """multi-goal_spread.py:114-118 (host helper on the synced positions)"""
-        delta_pos = agent1.state.p_pos - agent2.state.p_pos
-        dist = np.sqrt(np.sum(np.square(delta_pos)))
-        dist_min = agent1.size + agent2.size
-        return True if dist < dist_min else False
+        gap = np.sqrt(np.sum(np.square(agent1.state.p_pos - agent2.state.p_pos)))
+        return bool(gap < agent1.size + agent2.size)
 
     def benchmark_data(self, agent, world):
-        """multi-goal_spread.py:95-111 - never wired by the trainers (info_callback=None)."""
-        rew = 0
+        """multi-goal_spread.py:95-111 -> (rew, collisions, min_dists, occupied_landmarks).  Never
+        wired by the trainers (info_callback=None, train_onpolicy.py:119); evaluated on the host
+        from the synced positions."""
+        pos = np.array([a.state.p_pos for a in world.agents])
+        lms = np.array([l.state.p_pos for l in world.landmarks])
+        nearest = np.sqrt(np.sum(np.square(pos[None, :, :] - lms[:, None, :]), axis=2)).min(axis=1)
+        rew, min_dists = 0, 0
+        for d in nearest:            # accumulate in landmark order like the reference's loop
+            min_dists += d
+            rew -= d
+        occupied_landmarks = int((nearest < 0.1).sum())
         collisions = 0
-        occupied_landmarks = 0
-        min_dists = 0
-        for l in world.landmarks:
-            dists = [np.sqrt(np.sum(np.square(a.state.p_pos - l.state.p_pos))) for a in world.agents]
-            min_dists += min(dists)
-            rew -= min(dists)
-            if min(dists) < 0.1:
-                occupied_landmarks += 1
         if agent.collide:
-            for a in world.agents:
-                if self.is_collision(a, agent):
-                    rew -= 1
-                    collisions += 1
+            collisions = sum(1 for a in world.agents if self.is_collision(a, agent))
+            rew -= collisions
         return (rew, collisions, min_dists, occupied_landmarks)

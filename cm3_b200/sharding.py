@@ -1,0 +1,180 @@
+"""Multi-GPU use of the env stepper: one process per GPU, the env batch cut into contiguous
+global-env-id ranges, no collective on the stepping path, and an optional all-gather of the
+rollout buffers for a learner that wants the whole batch on every GPU.
+
+The reference has no counterpart: it runs one env instance per process and its only fan-out is one
+process per seed without communication (alg/train_multiprocess.py:31-43).  What is here stands
+where a data-parallel learner built on the reference's loop (alg/train_onpolicy.py:302-350) would
+exchange its workers' rollouts.
+
+torch.distributed is the plumbing (rendezvous, NCCL / gloo collectives, symmetric-memory handle
+exchange); the stepping and, in "peer" mode, the gather itself are this repo's kernels.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def split_envs(total_envs, world):
+    """Contiguous ranges [(start, count)] * world; the first total % world ranks take one extra."""
+    total_envs, world = int(total_envs), int(world)
+    if world < 1 or total_envs < world:
+        raise ValueError("need 1 <= world <= total_envs (got world=%d, total_envs=%d)" % (world, total_envs))
+    base, extra = divmod(total_envs, world)
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((start, n))
+        start += n
+    return out
+
+
+class EnvShard(object):
+    """The env-id range owned by this rank.  rank / world default to the initialised process
+    group, else to torchrun's RANK / WORLD_SIZE, else to a single process."""
+
+    def __init__(self, total_envs, rank=None, world=None, local_rank=None):
+        if rank is None or world is None:
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+            else:
+                rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        if not 0 <= rank < world:
+            raise ValueError("rank %d outside world %d" % (rank, world))
+        self.total_envs, self.rank, self.world = int(total_envs), int(rank), int(world)
+        self.ranges = split_envs(total_envs, world)
+        self.start, self.count = self.ranges[rank]
+        self.local_rank = int(os.environ.get("LOCAL_RANK", rank)) if local_rank is None else int(local_rank)
+        self.device = "cuda:%d" % self.local_rank
+
+    @property
+    def uniform(self):
+        return self.total_envs % self.world == 0
+
+    def owner_of(self, env_id):
+        for r, (s, n) in enumerate(self.ranges):
+            if s <= env_id < s + n:
+                return r, env_id - s
+        raise IndexError(env_id)
+
+    def __repr__(self):
+        return "EnvShard(rank %d/%d: envs [%d, %d) of %d)" % (self.rank, self.world, self.start,
+                                                              self.start + self.count, self.total_envs)
+
+
+def all_gather_rollout(local, shard, group=None, time_major=True):
+    """Collective all-gather of rollout fields.  `local` maps field -> [T, B_local, ...] tensor
+    (same T and trailing shape on every rank, B_local = shard.count which must be uniform).
+    Returns field -> [T, B_total, ...] (time_major, one permuting copy after the collective) or
+    field -> [world, T, B_local, ...] (the collective's native layout, no copy).  Works on any
+    backend (NCCL on GPUs; gloo in the CPU tests)."""
+    if not shard.uniform:
+        raise ValueError("all_gather_rollout needs total_envs divisible by the world size")
+    out = {}
+    for k, x in local.items():
+        x = x.contiguous()
+        if x.shape[1] != shard.count:
+            raise ValueError("%s: second dim %d != shard.count %d" % (k, x.shape[1], shard.count))
+        g = torch.empty((shard.world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        if shard.world == 1:
+            g[0].copy_(x)
+        else:
+            # concatenation form [world * T, ...]: accepted by NCCL and gloo alike
+            dist.all_gather_into_tensor(g.view((shard.world * x.shape[0],) + tuple(x.shape[1:])), x, group=group)
+        if time_major:
+            T = x.shape[0]
+            perm = (1, 0) + tuple(range(2, g.dim()))
+            g = g.permute(*perm).reshape((T, shard.total_envs) + tuple(x.shape[2:]))
+        out[k] = g
+    return out
+
+
+class RolloutAllGather(object):
+    """T fused env steps on this rank's shard with the outputs of ALL ranks delivered as
+    field -> [T, total_envs, ...] on every GPU.
+
+    mode "peer": the rollout buffers live in symmetric memory (every rank can address every
+        rank's buffer over NVLink); cm3_*_rollout_gather stores each output element straight
+        into all `world` buffers at this shard's env offset - compute and all-gather are ONE
+        kernel, there is no local staging buffer and no collective launch.  A barrier on the
+        stream publishes the stores.
+    mode "nccl": local rollout, then ncclAllGather per field (+ a permuting copy to time-major).
+    mode "auto": "peer" when symmetric memory can be set up for the group, else "nccl".
+    """
+
+    def __init__(self, env, T, shard=None, group=None, mode="auto", fields=None):
+        self.env, self.T = env, int(T)
+        self.shard = shard or EnvShard(env.B if not dist.is_initialized() else env.B * dist.get_world_size())
+        if self.shard.count != env.B:
+            raise ValueError("env.B (%d) != shard.count (%d)" % (env.B, self.shard.count))
+        if env.env_id_offset != self.shard.start:
+            raise ValueError("env.env_id_offset (%d) != shard.start (%d)" % (env.env_id_offset, self.shard.start))
+        self.group = group
+        self.fields = tuple(fields) if fields is not None else tuple(env.field_shapes().keys())
+        self.mode = mode
+        self._hdl = None
+        if mode in ("auto", "peer"):
+            try:
+                self._setup_peer()
+                self.mode = "peer"
+            except Exception as e:  # noqa: BLE001 - symmetric memory is an optional capability
+                if mode == "peer":
+                    raise
+                self.mode, self.peer_error = "nccl", repr(e)
+        if self.mode == "nccl":
+            self.local = {k: v for k, v in env.alloc_outputs(self.T).items() if k in self.fields}
+
+    # ------------------------------------------------------------------ peer mode
+    def _field_layout(self):
+        """Byte offsets of the [T, total_envs, ...] arrays inside one symmetric allocation."""
+        shapes = self.env.field_shapes()
+        layout, off = {}, 0
+        for k in self.fields:
+            dt = torch.uint8 if k == "done" else self.env.dtype
+            shp = (self.T, self.shard.total_envs) + tuple(shapes[k][1:])
+            nbytes = int(torch.Size(shp).numel()) * torch.empty((), dtype=dt).element_size()
+            layout[k] = (off, shp, dt)
+            off += (nbytes + 255) // 256 * 256
+        return layout, off
+
+    def _setup_peer(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not self.shard.uniform:
+            raise ValueError("peer mode needs total_envs divisible by the world size")
+        if self.shard.world > 8:
+            raise ValueError("peer mode addresses at most 8 GPUs (one NVSwitch node)")
+        layout, total = self._field_layout()
+        dev = self.env.device
+        buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, grp)
+        self._buf, self._hdl, self._layout = buf, hdl, layout
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.gathered = {k: buf[off:off + int(torch.Size(shp).numel()) * torch.empty((), dtype=dt).element_size()]
+                         .view(dt).view(shp) for k, (off, shp, dt) in layout.items()}
+        self._dst_ptrs = [{k: ptrs[r] + layout[k][0] for k in self.fields} for r in range(self.shard.world)]
+
+    # ------------------------------------------------------------------ API
+    def rollout(self, actions=None, seed=0, t0=0, auto_reset=False, time_major=True):
+        env = self.env
+        if self.mode == "peer":
+            self._hdl.barrier()  # every rank is done reading the previous contents
+            env.rollout_gather(self.T, self._dst_ptrs, self.shard.total_envs, self.shard.start,
+                               actions=actions, seed=seed, t0=t0, auto_reset=auto_reset)
+            self._hdl.barrier()  # all ranks' stores have landed
+            return self.gathered
+        env.rollout(self.T, actions=actions, seed=seed, t0=t0, auto_reset=auto_reset, out=self.local)
+        return all_gather_rollout(self.local, self.shard, self.group, time_major=time_major)
+
+    def bytes_moved_per_rollout(self):
+        """Bytes this rank sends to peers (peer mode: stores over NVLink; nccl: all-gather send)."""
+        shapes = self.env.field_shapes()
+        per_env = 0
+        for k in self.fields:
+            el = 1 if k == "done" else (8 if self.env.dtype == torch.float64 else 4)
+            n = 1
+            for d in shapes[k][1:]:
+                n *= d
+            per_env += n * el
+        return per_env * self.env.B * self.T * (self.shard.world - 1)

@@ -47,6 +47,7 @@ class VecParticle(object):
         cfg.real = L.REAL_F64 if dtype == torch.float64 else L.REAL_F32
         cfg.device = dev_index
         cfg.env_id_offset = int(env_id_offset)
+        self.env_id_offset = int(env_id_offset)
         for i in range(self.N):
             cfg.agents_x[i] = float(config["agents_x"][i])
             cfg.agents_y[i] = float(config["agents_y"][i])
@@ -179,6 +180,25 @@ class VecParticle(object):
             out = dict(out)
             out["actions"] = rec
         return out
+
+    def rollout_gather(self, T, dst_ptrs, dst_B, dst_env0, actions=None, seed=0, t0=0,
+                       auto_reset=False):
+        """Fused rollout + all-gather (cm3_particle_rollout_gather): like rollout(), but every output element is stored
+        to each destination in `dst_ptrs` - a list (one entry per GPU, at most 8) of dicts
+        field -> raw device pointer of a [T, dst_B, ...] array, typically the symmetric-memory
+        rollout buffers of all ranks (cm3_b200.sharding.RolloutAllGather).  This shard's envs land
+        at rows [dst_env0, dst_env0 + B).  Fields missing from the dicts are not written."""
+        T = int(T)
+        if not 1 <= len(dst_ptrs) <= L.MAX_DST:
+            raise ValueError("1..%d destinations" % L.MAX_DST)
+        a = None if actions is None else self._actions_tensor(actions, (T,))
+        arr = (L.ParticleOutputs * len(dst_ptrs))()
+        for i, d in enumerate(dst_ptrs):
+            arr[i] = L.ParticleOutputs(*[(C.c_void_p(int(d[f])) if d.get(f) else None) for f in FIELDS])
+        L.check(self.lib.cm3_particle_rollout_gather(self._h, C.byref(self._st), _ptr(a), int(seed) & (2**64 - 1), int(t0), T,
+                            1 if auto_reset else 0, None, len(dst_ptrs), arr, int(dst_B),
+                            int(dst_env0), self._stream()))
+        self._keep = (a, arr)
 
     def step_host(self, actions, fields=FIELDS):
         if self._host is None:
