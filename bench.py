@@ -4,13 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ck2|pa4|pa3|pm2|ck1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over the whole env batch of a GPU: ONE launch of the fused
-step kernel (action apply -> move/collect or dynamics+contact -> reward -> observation assembly)
-for B envs, with in-kernel episode reset, reading a pre-generated int8 action slice resident in
-HBM and writing its outputs into slot (t mod ring) of a rollout ring [ring][B][...] that is larger
-than L2 (so outputs of a step are not absorbed by the 126 MB L2 when the next step runs).
-Timing: CUDA events on the launching stream around exactly K launches (replayed from a CUDA graph
-so the host is out of the loop), barrier + synchronize on both sides, max over ranks.
+One "step" = one pass of the hot path over the whole env batch of a GPU: action apply -> move/collect
+or dynamics+contact -> reward -> observation assembly for B envs, with in-kernel episode reset,
+reading that step's int8 action slice from a pre-generated [33][B][N] stream resident in HBM and
+writing EVERY output field of the step to HBM.
+
+  --mode fused (default, the headline `value`): the 33 steps of an episode are one launch of the
+      step kernel (state stays in registers between steps); outputs go to a rollout buffer
+      [33][B][...] that is larger than L2 (CK2: 2.06 GB) and is overwritten by the next launch.
+  --mode step (reported under extra.per_step_launches): one launch per step - what a policy in
+      the loop needs - replayed from a CUDA graph, outputs into slot (t mod ring) of a ring > L2.
+
+Timing: CUDA events on the launching stream around exactly K steps, barrier + synchronize on both
+sides, max over ranks.
 
 Prints ONE JSON line (rank 0).  Extra keys beyond the driver contract:
   roofline      dominant kernel vs the measured HBM copy peak (MEASURED_PEAKS.json)
@@ -217,8 +223,64 @@ class StepRunner(object):
             self.launch(t)
 
 
+class FusedRunner(object):
+    """K steps as K/T launches of the T-step kernel reading the pre-generated action stream."""
+
+    def __init__(self, env, T, seed):
+        import torch
+        self.env, self.T = env, T
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        self.actions = torch.randint(0, 5, (T, env.B, env.N), generator=g, dtype=torch.int8).to(env.device)
+        self.out = env.alloc_outputs(T)
+        self.launches = 0
+
+    def capture(self):
+        pass
+
+    def run(self, k):
+        n_full, rem = divmod(k, self.T)
+        for _ in range(n_full):
+            self.env.rollout(self.T, actions=self.actions, auto_reset=True, out=self.out)
+        if rem:
+            self.env.rollout(rem, actions=self.actions[:rem], auto_reset=True,
+                             out={f: v[:rem] for f, v in self.out.items()})
+        self.launches += n_full + (1 if rem else 0)
+
+
 def bytes_per_env_step(env):
     return env.bytes_per_env_step()
+
+
+def timed_steps(runner, K, W, world, device, local_rank, sample_clocks=True):
+    """W warm-up steps, then exactly K timed steps; returns (ms max over ranks, clocks)."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    runner.run(W)
+    sampler = ClockSampler(local_rank) if sample_clocks else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.start()
+    e0.record()
+    runner.run(K)
+    e1.record()
+    if sampler:
+        sampler.sample()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, clocks
 
 
 class GatherRunner(object):
@@ -261,69 +323,64 @@ def run_gpu(args):
     # ring larger than L2 (126 MB): at least 33 slots and >= 512 MB of outputs
     ring = max(MAX_STEPS, int(np.ceil(512e6 / (bpe * B))))
     gather_mode = None
+    T = MAX_STEPS
+    W = max(W, 3)
+    out_b = env.out_bytes_per_env_step()
+    state_b = bpe - out_b - spec["n"]
+    fused_bpe = out_b + spec["n"] + state_b / T
+    launch_cfg = None
     if args.gather != "none":
         from cm3_b200.sharding import EnvShard
-        T = MAX_STEPS
         K = max(T, K // T * T)
-        W = max(T, (max(W, 3) + T - 1) // T * T)
+        W = (W + T - 1) // T * T
         runner = GatherRunner(env, EnvShard(world * B, rank=rank, world=world, local_rank=local_rank), T, args.gather)
         gather_mode = runner.mode
+        mode = "gather"
+    elif args.mode == "fused":
+        runner = FusedRunner(env, T, SEED + rank)
+        mode = "fused"
     else:
         runner = StepRunner(env, spec, ring, SEED + rank)
+        mode = "step"
     runner.capture()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    runner.run(max(W, 3))
-    sampler = ClockSampler(local_rank)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.start()
-    e0.record()
-    runner.run(K)
-    e1.record()
-    sampler.sample()
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, clocks = timed_steps(runner, K, W, world, device, local_rank)
     value = world * B * spec["n"] * K / (ms * 1e-3)
     peak, peak_src = hbm_peak()
-    launch_us = ms * 1e3 / K
-    achieved = bpe * B / (launch_us * 1e-6) / 1e9
-    kernel_key = "%s_step" % args.workload
+    step_us = ms * 1e3 / K
+    if mode == "step":
+        eff_bpe, launches, launch_us = bpe, K, step_us
+        launch_cfg = {"launch": "1 kernel launch per step, replayed from a CUDA graph of %d steps" % ring,
+                      "rollout_ring_slots": ring,
+                      "l2": "outputs go to a %d-slot rollout ring of %.0f MB (> 126 MB L2); no explicit flush" % (ring, ring * bpe * B / 1e6)}
+    else:
+        eff_bpe, launches = fused_bpe, (K + T - 1) // T
+        launch_us = ms * 1e3 / launches
+        launch_cfg = {"launch": "1 kernel launch per %d steps (one episode): state stays in registers between the steps of a launch" % T,
+                      "l2": "every step writes all its outputs to a [%d][B] rollout buffer of %.0f MB (> 126 MB L2), overwritten by the next launch; no explicit flush" % (T, out_b * B * T / 1e6)}
+    achieved = eff_bpe * B / (step_us * 1e-6) / 1e9
+    kernel_key = "%s_%s" % (args.workload, "step" if mode == "step" else "rollout")
+    kname = {"ck2": "checkers_kernel<3,8,2,2,float,float>", "ck1": "checkers_kernel<3,8,2,1,float,float>",
+             "pa4": "particle_kernel<4,float>", "pa3": "particle_kernel<3,float>", "pm2": "particle_kernel<2,float>"}[args.workload]
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 bitboard state, f32 outputs" if spec["kind"] == "checkers" else "f32",
         "data": "synthetic",
-        "config": {"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"],
-                   "actions": "uniform int8 in 0..4 pre-generated in HBM", "auto_reset": True,
-                   "rollout_ring_slots": ring,
-                   "l2": "outputs go to a %d-slot rollout ring of %.0f MB (> 126 MB L2); no explicit flush" % (ring, ring * bpe * B / 1e6),
-                   "launch": "1 kernel launch per step, replayed from a CUDA graph of %d steps" % ring,
-                   "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world},
+        "config": dict({"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"], "mode": mode,
+                        "actions": "uniform int8 in 0..4, a [33][B][N] stream pre-generated in HBM and read by every step",
+                        "auto_reset": True,
+                        "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world}, **launch_cfg),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(kernel_key),
-                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": bpe,
-                     "bytes_per_launch": bpe * B, "launch_us": launch_us,
-                     "kernel": "checkers_kernel<3,8,2,2,float>" if args.workload == "ck2" else "%s step kernel" % args.workload},
-        "gpu_launches": K,
+                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": eff_bpe,
+                     "bytes_per_launch": eff_bpe * B * (K / launches), "launch_us": launch_us, "kernel": kname},
+        "gpu_launches": launches,
         "clocks": clocks,
     }
     if gather_mode is not None:
-        T = MAX_STEPS
-        el = 8 if env.dtype == torch.float64 else 4
-        out_b = sum(int(np.prod(sh[1:])) for k, sh in env.field_shapes().items() if k != "done") * el + 1
         sent = out_b * B * (world - 1)  # bytes this GPU delivers to its peers per env step
+        launch_us = step_us
         out["gpu_launches"] = K // T
         out["config"].update({"launch": "1 launch per %d fused env steps, device Philox actions" % T,
                               "actions": "Philox4x32-10 on the device, keyed by (seed, global env id, step)",
@@ -342,7 +399,9 @@ def run_gpu(args):
         pass  # the collective run reports the kernel-side number only
     elif rank == 0 and not args.no_extras:
         out["e2e"] = measure_e2e(env, spec, args)
-        out["extra"] = measure_extras(env, spec, args, peak)
+        out["extra"] = measure_extras(env, spec, args, peak, mode, world, device, local_rank, ring)
+        if spec["kind"] == "checkers":
+            out["extra"]["e2e_int8_tiles"] = measure_e2e_int8(spec, args, device)
         if world == 1:
             out["cpu_baseline"] = cpu_baseline(spec, args)
     elif rank == 0:
@@ -378,11 +437,35 @@ def measure_e2e(env, spec, args):
             "note": "no auto-reset on this path (reference semantics); PCIe-bound: %.1f MB D2H per step" % (bo / 1e6)}
 
 
-def measure_extras(env, spec, args, peak):
+def measure_e2e_int8(spec, args, device):
+    """Checkers only: the same host-buffer call with grid / obs_self_t delivered as int8 (lossless:
+    their values are always in {-1, 0, +1}) - a quarter of the tile bytes over PCIe."""
+    import torch
+    from cm3_b200 import VecCheckers
+    env = VecCheckers(args.envs, device=device, tile_dtype=torch.int8, **spec["ctor"])
+    env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
+    res = measure_e2e(env, spec, args)
+    res["api"] = "VecCheckers(tile_dtype=int8).step_host -> cm3_checkers_step_host, cfg.tile = CM3_TILE_I8"
+    return res
+
+
+def measure_extras(env, spec, args, peak, mode="fused", world=1, device="cuda:0", local_rank=0, ring=MAX_STEPS):
     import torch
     extra = {}
     B, N = env.B, env.N
     bpe = bytes_per_env_step(env)
+    if mode == "fused":
+        # (0) the same workload as one launch PER STEP (what a policy in the loop needs)
+        runner = StepRunner(env, spec, ring, SEED)
+        runner.capture()
+        K = max(ring, args.steps // ring * ring)
+        ms, _ = timed_steps(runner, K, ring, 1, device, local_rank, sample_clocks=False)
+        ach = bpe * B * K / (ms * 1e-3) / 1e9
+        extra["per_step_launches"] = {"value": B * N * K / (ms * 1e-3), "unit": UNIT, "launches": K,
+                                      "us_per_step": ms * 1e3 / K, "achieved_gbs": ach, "frac": ach / peak,
+                                      "algorithmic_bytes_per_env_step": bpe, "rollout_ring_slots": ring,
+                                      "note": "one launch per step from a CUDA graph with programmatic dependent launch; outputs to a %d-slot ring of %.0f MB (> L2); this GPU only" % (ring, ring * bpe * B / 1e6)}
+        del runner
     # (1) fused T-step rollout kernel: state in registers, Philox actions, one launch per 33 steps
     T = MAX_STEPS
     out = env.alloc_outputs(T)
@@ -397,12 +480,11 @@ def measure_extras(env, spec, args, peak):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    el = 8 if env.dtype == torch.float64 else 4
-    out_bytes = sum(int(np.prod(s[1:])) for k, s in env.field_shapes().items() if k != "done") * el + 1
+    out_bytes = env.out_bytes_per_env_step()
     state_bytes = bpe - out_bytes - N
     fused_bpe = out_bytes + state_bytes / T  # actions come from Philox: no action bytes
     ach = fused_bpe * B * T * reps / (ms * 1e-3) / 1e9
-    extra["fused_rollout_T33"] = {"value": B * N * T * reps / (ms * 1e-3), "unit": UNIT, "launches": reps,
+    extra["fused_rollout_T33_philox"] = {"value": B * N * T * reps / (ms * 1e-3), "unit": UNIT, "launches": reps,
                                   "ms_per_launch": ms / reps, "achieved_gbs": ach, "frac": ach / peak,
                                   "algorithmic_bytes_per_env_step": fused_bpe,
                                   "note": "one launch = 33 env steps, device Philox actions, in-kernel reset, outputs to a [33][B] rollout buffer (%.0f MB > L2)" % (out_bytes * B * T / 1e6)}
@@ -473,6 +555,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--mode", default="fused", choices=["fused", "step"],
+                    help="fused: one launch per 33-step episode (headline); step: one launch per step")
     ap.add_argument("--gather", default="none", choices=["none", "nccl", "peer", "auto"],
                     help="all-gather the rollout buffers to every GPU (BASELINE.json configs[3])")
     args = ap.parse_args()

@@ -7,6 +7,7 @@ from .build import library_path
 MAX_AGENTS = 4
 MAX_DST = 8
 REAL_F32, REAL_F64 = 0, 1
+TILE_REAL, TILE_I8 = 0, 1
 
 STATUS_NAMES = {0: "CM3_OK", -1: "CM3_ERR_BAD_ARG", -2: "CM3_ERR_BAD_SHAPE", -3: "CM3_ERR_CUDA",
                 -4: "CM3_ERR_UNSUPPORTED", -5: "CM3_ERR_NO_DEVICE"}
@@ -23,7 +24,7 @@ class CheckersConfig(C.Structure):
                 ("n_agents", C.c_int32), ("max_steps", C.c_int32),
                 ("agents_r", C.c_int32 * MAX_AGENTS), ("agents_c", C.c_int32 * MAX_AGENTS),
                 ("num_envs", C.c_int32), ("real", C.c_int32), ("device", C.c_int32),
-                ("reserved", C.c_int32), ("env_id_offset", C.c_int64)]
+                ("tile", C.c_int32), ("env_id_offset", C.c_int64)]
 
 
 class CheckersState(C.Structure):

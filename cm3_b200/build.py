@@ -8,7 +8,8 @@ CSRC = os.path.join(HERE, "csrc")
 # two halves of its template instantiations build in parallel
 UNITS = [("api.cu", (), "api"), ("particle.cu", (), "particle"),
          ("checkers.cu", ("CM3_CK_REAL=0",), "checkers_f32"),
-         ("checkers.cu", ("CM3_CK_REAL=1",), "checkers_f64")]
+         ("checkers.cu", ("CM3_CK_REAL=1",), "checkers_f64"),
+         ("checkers.cu", ("CM3_CK_REAL=2",), "checkers_f32_i8")]
 SOURCES = ["api.cu", "checkers.cu", "particle.cu"]
 HEADERS = ["common.cuh", "params.cuh", os.path.join("..", "..", "include", "cm3env.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]

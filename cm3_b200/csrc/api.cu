@@ -143,9 +143,14 @@ int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out) {
         return CM3_ERR_BAD_SHAPE;
     }
     if (O < 1 || N < 1 || cfg->num_envs < 1 || cfg->max_steps < 0 || cfg->max_steps > 0xFFFFFF ||
-        (cfg->real != CM3_REAL_F32 && cfg->real != CM3_REAL_F64)) {
-        set_error("bad n_obs/n_agents/num_envs/max_steps/real");
+        (cfg->real != CM3_REAL_F32 && cfg->real != CM3_REAL_F64) ||
+        (cfg->tile != CM3_TILE_REAL && cfg->tile != CM3_TILE_I8)) {
+        set_error("bad n_obs/n_agents/num_envs/max_steps/real/tile");
         return CM3_ERR_BAD_ARG;
+    }
+    if (cfg->tile == CM3_TILE_I8 && cfg->real != CM3_REAL_F32) {
+        set_error("int8 tiles are compiled for float outputs only");
+        return CM3_ERR_UNSUPPORTED;
     }
     if (N > CM3_MAX_AGENTS || !checkers_geometry_supported(R, C, O, N)) {
         set_error("no compiled Checkers kernel for n_rows=%d n_columns=%d n_obs=%d n_agents=%d", R, C, O, N);
@@ -216,7 +221,7 @@ static int ck_fill(cm3_checkers_t h, const cm3_checkers_state *st, const cm3_che
 static int ck_launch(cm3_checkers_t h, const CkParams &p, void *stream) {
     DeviceGuard g(h->cfg.device);
     if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
-    return checkers_launch(h->cfg.n_rows, h->cfg.n_columns, h->cfg.n_obs, h->cfg.n_agents, h->cfg.real, p,
+    return checkers_launch(h->cfg.n_rows, h->cfg.n_columns, h->cfg.n_obs, h->cfg.n_agents, h->cfg.real, h->cfg.tile, p,
                            (cudaStream_t)stream);
 }
 
@@ -278,14 +283,15 @@ int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const
     cudaStream_t s = (cudaStream_t)stream;
     const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
     const size_t W = 2 * h->cfg.n_obs + 1, L = 2 * (N > 1 ? N - 1 : 1);
+    const size_t ts = h->cfg.tile == CM3_TILE_I8 ? 1 : rs;
     CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
     int rc = cm3_checkers_step(h, st, actions_dev, od, stream);
     if (rc != CM3_OK) return rc;
     struct { void *dst; const void *src; size_t bytes; } cp[] = {
-        {oh->grid, od->grid, B * h->cfg.n_rows * (h->cfg.n_columns + 1) * 2 * rs},
+        {oh->grid, od->grid, B * h->cfg.n_rows * (h->cfg.n_columns + 1) * 2 * ts},
         {oh->vec, od->vec, B * N * 4 * rs},
         {oh->obs_others, od->obs_others, B * N * L * rs},
-        {oh->obs_self_t, od->obs_self_t, B * N * W * W * 3 * rs},
+        {oh->obs_self_t, od->obs_self_t, B * N * W * W * 3 * ts},
         {oh->obs_self_v, od->obs_self_v, B * N * 4 * rs},
         {oh->reward, od->reward, B * rs},
         {oh->local_rewards, od->local_rewards, B * N * rs},

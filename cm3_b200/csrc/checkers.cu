@@ -25,7 +25,7 @@
 #include "params.cuh"
 
 #ifndef CM3_CK_REAL
-#error "compile with -DCM3_CK_REAL=0 (float kernels) and -DCM3_CK_REAL=1 (double kernels)"
+#error "compile with -DCM3_CK_REAL=0 (float), =1 (double) and =2 (float + int8 tiles)"
 #endif
 
 namespace cm3 {
@@ -44,6 +44,11 @@ template <> __device__ __forceinline__ float tri_value<float>(uint32_t nz, uint3
 }
 template <> __device__ __forceinline__ double tri_value<double>(uint32_t nz, uint32_t neg) {
     return (double)((int)nz - 2 * (int)neg);
+}
+
+// compact tiles: the same {-1, 0, +1} as signed bytes (lossless; 4x fewer bytes over HBM / PCIe)
+template <> __device__ __forceinline__ int8_t tri_value<int8_t>(uint32_t nz, uint32_t neg) {
+    return (int8_t)(nz | (neg * 0xFEu));
 }
 
 template <typename Real> __device__ __forceinline__ void store4(Real *p, Real a, Real b, Real c, Real d);
@@ -69,7 +74,9 @@ template <int N> __device__ __forceinline__ int pick(const int (&v)[N], int idx)
     return r;
 }
 
-template <int R, int C, int O, int N, typename Real>
+// Real: type of the small vectors and rewards; Tile: element type of the two bulky outputs (the
+// per-agent window and the global grid) - Real, or int8_t for the compact encoding.
+template <int R, int C, int O, int N, typename Real, typename Tile = Real>
 struct CkGeom {
     static constexpr int TR = R + 2 * O;
     static constexpr int TC = C + 2 * O + 1;
@@ -80,8 +87,8 @@ struct CkGeom {
     static constexpr int NP = (N == 3) ? 4 : N;  // lanes reserved per env
     static constexpr int EW = kWarp / NP;        // envs per warp
     static constexpr int CNT = R * C / 2 + 1;
-    static constexpr int kWinBytes = round_up(EW * N * WW3 * (int)sizeof(Real), 16);
-    static constexpr int kGridBytes = round_up(EW * G * (int)sizeof(Real), 16);
+    static constexpr int kWinBytes = round_up(EW * N * WW3 * (int)sizeof(Tile), 16);
+    static constexpr int kGridBytes = round_up(EW * G * (int)sizeof(Tile), 16);
     static constexpr int kWarpStageBytes = kWinBytes + kGridBytes;
     static constexpr int kLutBytes = round_up((TR + TC + CNT) * (int)sizeof(Real), 128);
     static constexpr int kSmemBytes = kLutBytes + kCkWarpsPerBlock * kWarpStageBytes;
@@ -102,10 +109,10 @@ struct CkGeom {
     }
 };
 
-template <int R, int C, int O, int N, typename Real>
+template <int R, int C, int O, int N, typename Real, typename Tile>
 __global__ void __launch_bounds__(kCkWarpsPerBlock *kWarp)
 checkers_kernel(const __grid_constant__ CkParams p) {
-    using Gm = CkGeom<R, C, O, N, Real>;
+    using Gm = CkGeom<R, C, O, N, Real, Tile>;
     constexpr int TR = Gm::TR, TC = Gm::TC, W = Gm::W, WW3 = Gm::WW3, G = Gm::G, L = Gm::L;
     constexpr int EW = Gm::EW;
     constexpr uint32_t CM = Gm::CM;
@@ -121,8 +128,8 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Real *stage_win = reinterpret_cast<Real *>(smem_raw + Gm::kLutBytes + warp * Gm::kWarpStageBytes);
-    Real *stage_grid = reinterpret_cast<Real *>(reinterpret_cast<unsigned char *>(stage_win) + Gm::kWinBytes);
+    Tile *stage_win = reinterpret_cast<Tile *>(smem_raw + Gm::kLutBytes + warp * Gm::kWarpStageBytes);
+    Tile *stage_grid = reinterpret_cast<Tile *>(reinterpret_cast<unsigned char *>(stage_win) + Gm::kWinBytes);
 
     const int tile = blockIdx.x * kCkWarpsPerBlock + warp;
     const int env0 = tile * EW;
@@ -177,7 +184,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         __syncwarp();
         // ---------------- window of agent a (get_obs, checkers.py:97-109)
         if (o0.obs_self_t != nullptr && valid) {
-            Real *win = stage_win + (e * N + a) * WW3;
+            Tile *win = stage_win + (e * N + a) * WW3;
             const int sh = my_c - O;  // leftmost window column, >= 0
 #pragma unroll
             for (int dr = 0; dr < W; ++dr) {
@@ -201,10 +208,10 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 const uint32_t ng2 = occ >> sh;
 #pragma unroll
                 for (int dc = 0; dc < W; ++dc) {
-                    Real *cell = win + (dr * W + dc) * 3;
-                    cell[0] = tri_value<Real>((nz0 >> dc) & 1u, (ng0 >> dc) & 1u);
-                    cell[1] = tri_value<Real>((nz1 >> dc) & 1u, (ng1 >> dc) & 1u);
-                    cell[2] = tri_value<Real>((nz2 >> dc) & 1u, (ng2 >> dc) & 1u);
+                    Tile *cell = win + (dr * W + dc) * 3;
+                    cell[0] = tri_value<Tile>((nz0 >> dc) & 1u, (ng0 >> dc) & 1u);
+                    cell[1] = tri_value<Tile>((nz1 >> dc) & 1u, (ng1 >> dc) & 1u);
+                    cell[2] = tri_value<Tile>((nz2 >> dc) & 1u, (ng2 >> dc) & 1u);
                 }
             }
         }
@@ -213,9 +220,9 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         if (o0.obs_self_t != nullptr) {
             fence_proxy_async();
             __syncwarp();
-            const uint32_t bytes = (uint32_t)(nenv * N * WW3 * sizeof(Real));
+            const uint32_t bytes = (uint32_t)(nenv * N * WW3 * sizeof(Tile));
             for (int d = 0; d < p.n_dst; ++d) {
-                Real *g = reinterpret_cast<Real *>(p.out[d].obs_self_t) + (slot + env0) * (size_t)(N * WW3);
+                Tile *g = reinterpret_cast<Tile *>(p.out[d].obs_self_t) + (slot + env0) * (size_t)(N * WW3);
                 if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
                     if (lane == 0) bulk_store(g, stage_win, bytes);
                     pending = true;
@@ -227,7 +234,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         }
         // ---------------- global grid (get_valid_grid, :66-76): lane a writes channel a
         if (o0.grid != nullptr && valid && a < 2) {
-            Real *gr = stage_grid + e * G;
+            Tile *gr = stage_grid + e * G;
 #pragma unroll
             for (int i = 0; i < R; ++i) {
                 const uint32_t rowrem = (uint32_t)(rem >> (i * C)) & CM;
@@ -241,7 +248,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                     for (int j = 0; j <= C; ++j) {
                         const uint32_t nzb = (j < C) ? ((cmask >> j) & 1u) : 0u;
                         const uint32_t ngb = (j < C) ? ((neg >> j) & 1u) : 0u;
-                        gr[(i * (C + 1) + j) * 2 + mych] = tri_value<Real>(nzb, ngb);
+                        gr[(i * (C + 1) + j) * 2 + mych] = tri_value<Tile>(nzb, ngb);
                     }
                 }
             }
@@ -249,9 +256,9 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         fence_proxy_async();
         __syncwarp();
         if (o0.grid != nullptr) {
-            const uint32_t bytes = (uint32_t)(nenv * G * sizeof(Real));
+            const uint32_t bytes = (uint32_t)(nenv * G * sizeof(Tile));
             for (int d = 0; d < p.n_dst; ++d) {
-                Real *g = reinterpret_cast<Real *>(p.out[d].grid) + (slot + env0) * (size_t)G;
+                Tile *g = reinterpret_cast<Tile *>(p.out[d].grid) + (slot + env0) * (size_t)G;
                 if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
                     if (lane == 1) bulk_store(g, stage_grid, bytes);
                     pending = true;
@@ -391,10 +398,10 @@ checkers_kernel(const __grid_constant__ CkParams p) {
 
 // ------------------------------------------------------------------------ host side
 
-template <int R, int C, int O, int N, typename Real>
+template <int R, int C, int O, int N, typename Real, typename Tile>
 static int launch_ck(const CkParams &p, cudaStream_t stream) {
-    using Gm = CkGeom<R, C, O, N, Real>;
-    auto kern = checkers_kernel<R, C, O, N, Real>;
+    using Gm = CkGeom<R, C, O, N, Real, Tile>;
+    auto kern = checkers_kernel<R, C, O, N, Real, Tile>;
     static bool attr_set[64] = {};
     int dev = 0;
     CM3_CUDA(cudaGetDevice(&dev));
@@ -417,15 +424,15 @@ static int launch_ck(const CkParams &p, cudaStream_t stream) {
     X(3, 8, 1)          \
     X(3, 8, 3)
 
-template <typename Real>
+template <typename Real, typename Tile>
 static int dispatch_ck(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
 #define X(r, c, o)                                                      \
     if (R == r && C == c && O == o) {                                   \
         switch (N) {                                                    \
-            case 1: return launch_ck<r, c, o, 1, Real>(p, stream);      \
-            case 2: return launch_ck<r, c, o, 2, Real>(p, stream);      \
-            case 3: return launch_ck<r, c, o, 3, Real>(p, stream);      \
-            case 4: return launch_ck<r, c, o, 4, Real>(p, stream);      \
+            case 1: return launch_ck<r, c, o, 1, Real, Tile>(p, stream);      \
+            case 2: return launch_ck<r, c, o, 2, Real, Tile>(p, stream);      \
+            case 3: return launch_ck<r, c, o, 3, Real, Tile>(p, stream);      \
+            case 4: return launch_ck<r, c, o, 4, Real, Tile>(p, stream);      \
             default: break;                                             \
         }                                                               \
     }
@@ -435,8 +442,8 @@ static int dispatch_ck(int R, int C, int O, int N, const CkParams &p, cudaStream
     return CM3_ERR_UNSUPPORTED;
 }
 
-// This file is compiled twice (cm3_b200/build.py): -DCM3_CK_REAL=0 instantiates the float kernels,
-// -DCM3_CK_REAL=1 the double ones; the two objects build in parallel.
+// This file is compiled three times (cm3_b200/build.py): -DCM3_CK_REAL=0 instantiates the float
+// kernels, =1 the double ones, =2 the float kernels with int8 tiles; the objects build in parallel.
 #if CM3_CK_REAL == 0
 bool checkers_geometry_supported(int R, int C, int O, int N) {
     if (N < 1 || N > CM3_MAX_AGENTS) return false;
@@ -448,16 +455,27 @@ bool checkers_geometry_supported(int R, int C, int O, int N) {
 }
 
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
-    return dispatch_ck<float>(R, C, O, N, p, stream);
+    return dispatch_ck<float, float>(R, C, O, N, p, stream);
 }
 
-int checkers_launch(int R, int C, int O, int N, int real, const CkParams &p, cudaStream_t stream) {
+int checkers_launch(int R, int C, int O, int N, int real, int tile, const CkParams &p, cudaStream_t stream) {
+    if (tile == CM3_TILE_I8) {
+        if (real != CM3_REAL_F32) {
+            set_error("int8 tiles are compiled for float outputs only");
+            return CM3_ERR_UNSUPPORTED;
+        }
+        return checkers_launch_f32_i8(R, C, O, N, p, stream);
+    }
     if (real == CM3_REAL_F64) return checkers_launch_f64(R, C, O, N, p, stream);
     return checkers_launch_f32(R, C, O, N, p, stream);
 }
-#else
+#elif CM3_CK_REAL == 1
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
-    return dispatch_ck<double>(R, C, O, N, p, stream);
+    return dispatch_ck<double, double>(R, C, O, N, p, stream);
+}
+#else
+int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
+    return dispatch_ck<float, int8_t>(R, C, O, N, p, stream);
 }
 #endif
 

@@ -78,7 +78,8 @@ struct PtParams {
 };
 
 bool checkers_geometry_supported(int R, int C, int O, int N);
-int checkers_launch(int R, int C, int O, int N, int real, const CkParams &p, cudaStream_t stream);
+int checkers_launch(int R, int C, int O, int N, int real, int tile, const CkParams &p, cudaStream_t stream);
+int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);

@@ -9,12 +9,17 @@
 //   MultiAgentEnv.step tail / reset   multiagent/environment.py:95-149
 //
 // Design:
-//  * one lane per (env, agent), agent-minor: lane = e*NP + a.  An env's agents sit in NP adjacent
-//    lanes, so the all-pairs contact force, the collision penalty and the env-level reductions
-//    (sum of rewards, all-reached, collision count) are width-NP warp shuffles - no shared memory;
-//  * state rows are (vel, pos) = the reference's global_state rows: one 16-byte load and store per
-//    lane, and consecutive lanes touch consecutive records: every global access of the kernel is
-//    a fully coalesced 16-byte (or 4-byte) per-lane access;
+//  * one THREAD per env, a warp per 32 consecutive envs, one warp per block.  All N <= 4 agents
+//    of an env live in the registers of one thread, so the all-pairs contact force, the collision
+//    penalty and the env-level reductions are plain register arithmetic: every pair is evaluated
+//    once (in the reference's pair order, core.py:145-154), there are no shuffles, and the
+//    65 536-env headline batch is 2048 warps = 14 per SM - one resident wave.  (Round-1's first
+//    version used one lane per (env, agent); ncu showed it latency-bound: 55 warps per SM in 2.3
+//    waves at 80 registers, every pair evaluated twice, 44 shuffles per step.)
+//  * the observation rows are written into a per-warp shared-memory tile whose layout IS the
+//    layout of the output arrays for those 32 envs and leave the SM as one TMA bulk store per
+//    field (cp.async.bulk.global.shared::cta): full-line HBM writes, like the Checkers kernel.
+//    Rewards / done flags go straight from registers (consecutive threads -> consecutive words);
 //  * arithmetic follows the reference operation by operation with round-to-nearest intrinsics
 //    (no FMA contraction, IEEE sqrt/div, no fast-math), in float (throughput mode) or double
 //    (free-running parity mode);
@@ -25,7 +30,7 @@
 
 namespace cm3 {
 
-constexpr int kPtThreads = 128;
+constexpr int kPtThreads = 32;  // one warp per block
 
 template <typename Real> struct Vec4;
 template <> struct Vec4<float> { using type = float4; };
@@ -139,25 +144,47 @@ __device__ __noinline__ ResetDraw<Real> draw_reset(const PtParams &p, unsigned l
     return d;
 }
 
+// get_collision_force for one pair in (or near) contact, core.py:180-196: the literal evaluation.
+// Out of line for the same reason as draw_reset: it is the rare path.
+template <typename Real> struct Force2 { Real x, y; };
+
+template <typename Real>
+__device__ __noinline__ Force2<Real> contact_force(Real ax, Real ay, Real bx, Real by, double dist_min, double k,
+                                                   Real cf, Real km) {
+    using Op = RealOps<Real>;
+    Real dx, dy, dist, x;
+    Contact<Real>::eval(ax, ay, bx, by, dist_min, k, dx, dy, dist, x);
+    const Real pen = Op::mul(logaddexp0<Real>(x), km);
+    return Force2<Real>{Op::mul(Op::div(Op::mul(cf, dx), dist), pen), Op::mul(Op::div(Op::mul(cf, dy), dist), pen)};
+}
+
+template <int N, typename Real>
+struct PtGeom {
+    static constexpr int NO = (N > 1) ? N - 1 : 1;  // "other" agents per agent
+    static constexpr int LO = 4 * NO;
+    static constexpr int kRowBytes = kWarp * N * 4 * (int)sizeof(Real);   // global_state / obs_self tile
+    static constexpr int kOthBytes = kWarp * N * LO * (int)sizeof(Real);  // obs_others tile
+    static constexpr int kSmemBytes = 2 * kRowBytes + kOthBytes;
+};
+
 template <int N, typename Real>
 __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_constant__ PtParams p) {
     using Op = RealOps<Real>;
-    constexpr int NP = (N == 3) ? 4 : N;
-    constexpr int EW = kWarp / NP;
-    constexpr int NO = (N > 1) ? N - 1 : 1;  // "other" agents per agent
-    constexpr int LO = 4 * NO;
-    constexpr unsigned kFullMask = 0xFFFFFFFFu;
+    using Gm = PtGeom<N, Real>;
+    constexpr int NO = Gm::NO, LO = Gm::LO;
 
     pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
-    const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * kPtThreads + threadIdx.x) >> 5;
-    const int env0 = gwarp * EW;
-    if (env0 >= p.B) return;  // warp-uniform
-    const int e = lane / NP, a = lane % NP;
-    const int gb = lane - a;  // first lane of my env's group
-    const int env = env0 + e;
-    const bool valid = (a < N) && (env < p.B);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Real *stage_gs = reinterpret_cast<Real *>(smem_raw);
+    Real *stage_os = reinterpret_cast<Real *>(smem_raw + Gm::kRowBytes);
+    Real *stage_oo = reinterpret_cast<Real *>(smem_raw + 2 * Gm::kRowBytes);
+
+    const int lane = threadIdx.x;
+    const int env0 = blockIdx.x * kWarp;
+    const int env = env0 + lane;
+    const int nenv = min(kWarp, p.B - env0);
+    const bool valid = lane < nenv;
     const size_t B = (size_t)p.B;
 
     // world constants, rounded to Real once on the host (no per-thread F2F conversions)
@@ -168,20 +195,20 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     const Real far2 = K.far2, near2 = K.near2;
     const bool unit_mass = (mass == (Real)1);  // x / 1 == x exactly: skip the IEEE division
 
-    // lane of the k-th "other" agent of my env, in index order (multi-goal_spread.py:149-152)
-    int src[NO];
-#pragma unroll
-    for (int k = 0; k < NO; ++k) src[k] = (N > 1) ? gb + k + (k >= a ? 1 : 0) : lane;
-
     pdl_wait();  // state written by the previous launch is visible from here on
 
-    // ---- state
-    Real vx = 0, vy = 0, px = (Real)(2 * lane), py = 0, lx = 0, ly = 0;  // idle lanes stay apart
+    // ---- state of my env: all agents in registers
+    Real vx[N], vy[N], px[N], py[N], lx[N], ly[N];
     int steps = 0, collisions = 0;
     uint32_t reached = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { vx[i] = 0; vy[i] = 0; px[i] = (Real)(2 * i); py[i] = 0; lx[i] = 0; ly[i] = 0; }
     if (valid) {
-        ld4<Real>(reinterpret_cast<const Real *>(p.sv) + ((size_t)env * N + a) * 4, vx, vy, px, py);
-        ld2<Real>(reinterpret_cast<const Real *>(p.landmarks) + ((size_t)env * N + a) * 2, lx, ly);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ld4<Real>(reinterpret_cast<const Real *>(p.sv) + ((size_t)env * N + i) * 4, vx[i], vy[i], px[i], py[i]);
+            ld2<Real>(reinterpret_cast<const Real *>(p.landmarks) + ((size_t)env * N + i) * 2, lx[i], ly[i]);
+        }
         steps = p.steps[env];
         collisions = p.collisions[env];
         reached = p.reached[env];
@@ -189,52 +216,75 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
 
     // multi-goal_spread.py:65-93 on Philox (or the injected host draws)
     auto reset_state = [&](unsigned long long counter) {
-        if (p.init_pos != nullptr && p.mode == kPtReset) {
-            const Real *ip = reinterpret_cast<const Real *>(p.init_pos) + ((size_t)env * N + a) * 2;
-            const Real *il = reinterpret_cast<const Real *>(p.init_landmarks) + ((size_t)env * N + a) * 2;
-            px = ip[0]; py = ip[1]; lx = il[0]; ly = il[1];
-        } else {
-            const ResetDraw<Real> d = draw_reset<Real>(p, (unsigned long long)(p.env_id_offset + env), counter,
-                                                       a < N ? a : 0);
-            px = d.px; py = d.py; lx = d.lx; ly = d.ly;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (p.init_pos != nullptr && p.mode == kPtReset) {
+                ld2<Real>(reinterpret_cast<const Real *>(p.init_pos) + ((size_t)env * N + i) * 2, px[i], py[i]);
+                ld2<Real>(reinterpret_cast<const Real *>(p.init_landmarks) + ((size_t)env * N + i) * 2, lx[i], ly[i]);
+            } else {
+                const ResetDraw<Real> d = draw_reset<Real>(p, (unsigned long long)(p.env_id_offset + env), counter, i);
+                px[i] = d.px; py[i] = d.py; lx[i] = d.lx; ly[i] = d.ly;
+            }
+            vx[i] = 0; vy[i] = 0;
         }
-        vx = 0; vy = 0; steps = 0; collisions = 0; reached = 0;  // :84-86, :93; environment.py:148
+        steps = 0; collisions = 0; reached = 0;  // :84-86, :93; environment.py:148
     };
 
-    // (vel, pos) of the other agents of my env, straight from their lanes
-    Real ovx[NO], ovy[NO], opx[NO], opy[NO];
-    auto gather_others = [&]() {
-#pragma unroll
-        for (int k = 0; k < NO; ++k) {
-            ovx[k] = __shfl_sync(kFullMask, vx, src[k]); ovy[k] = __shfl_sync(kFullMask, vy, src[k]);
-            opx[k] = __shfl_sync(kFullMask, px, src[k]); opy[k] = __shfl_sync(kFullMask, py, src[k]);
-        }
-    };
+    bool pending = false;  // bulk stores whose shared-memory source may still be in flight
+    const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
+    const PtOut &o0 = p.out[0];
 
     // observations of the current state -> outputs of slot t (multi-goal_spread.py:145-154,
-    // environment.py:113-116); needs gather_others() of the current state
-    const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
+    // environment.py:113-116)
     auto emit = [&](int t) {
-        if (!valid) return;
-        const size_t rec = ((size_t)t * OB + oe0 + env) * N + a;
-        Real dvx[NO], dvy[NO], dpx[NO], dpy[NO];
-#pragma unroll
-        for (int k = 0; k < NO; ++k) {  // N == 1: "others" is the agent itself, :148-153
-            dvx[k] = Op::sub(ovx[k], vx); dvy[k] = Op::sub(ovy[k], vy);
-            dpx[k] = Op::sub(opx[k], px); dpy[k] = Op::sub(opy[k], py);
+        if (pending) {
+            if (lane == 0) bulk_wait_read();
         }
-        // n_dst > 1 (rollout_gather): the same records go to the rollout buffers of every GPU of
-        // the node - peer memory over NVLink
-        for (int d = 0; d < p.n_dst; ++d) {
-            const PtOut &o = p.out[d];
-            if (o.global_state != nullptr) st4<Real>(reinterpret_cast<Real *>(o.global_state) + rec * 4, vx, vy, px, py);
-            if (o.obs_self != nullptr) st4<Real>(reinterpret_cast<Real *>(o.obs_self) + rec * 4, vx, vy, px, py);
-            if (o.obs_others != nullptr) {
-                Real *oo = reinterpret_cast<Real *>(o.obs_others) + rec * LO;
+        __syncwarp();
+        if (valid) {
 #pragma unroll
-                for (int k = 0; k < NO; ++k) st4<Real>(oo + 4 * k, dvx[k], dvy[k], dpx[k], dpy[k]);
+            for (int i = 0; i < N; ++i) {
+                if (o0.global_state != nullptr) st4<Real>(stage_gs + (lane * N + i) * 4, vx[i], vy[i], px[i], py[i]);
+                if (o0.obs_self != nullptr) st4<Real>(stage_os + (lane * N + i) * 4, vx[i], vy[i], px[i], py[i]);
+                if (o0.obs_others != nullptr) {
+                    Real *oo = stage_oo + (lane * N + i) * LO;
+                    if (N == 1) {  // "others" is the agent itself, :148-153
+                        st4<Real>(oo, Op::sub(vx[0], vx[0]), Op::sub(vy[0], vy[0]), Op::sub(px[0], px[0]),
+                                  Op::sub(py[0], py[0]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NO; ++k) {
+                            const int j = k + (k >= i ? 1 : 0);  // compile-time after unrolling
+                            st4<Real>(oo + 4 * k, Op::sub(vx[j], vx[i]), Op::sub(vy[j], vy[i]), Op::sub(px[j], px[i]),
+                                      Op::sub(py[j], py[i]));
+                        }
+                    }
+                }
             }
         }
+        fence_proxy_async();
+        __syncwarp();
+        pending = false;
+        const size_t row0 = (size_t)t * OB + oe0 + env0;
+        // one staged tile per field, n_dst bulk stores each: with rollout_gather the destinations
+        // are the rollout buffers of every GPU of the node (peer memory over NVLink)
+        auto put = [&](char *PtOut::*field, const Real *stage, int per_env) {
+            if (o0.*field == nullptr) return;
+            const uint32_t bytes = (uint32_t)(nenv * per_env * sizeof(Real));
+            for (int d = 0; d < p.n_dst; ++d) {
+                Real *g = reinterpret_cast<Real *>(p.out[d].*field) + row0 * (size_t)per_env;
+                if (nenv == kWarp && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+                    if (lane == 0) bulk_store(g, stage, bytes);
+                    pending = true;
+                } else {
+                    for (int idx = lane; idx < nenv * per_env; idx += kWarp) g[idx] = stage[idx];
+                }
+            }
+        };
+        put(&PtOut::obs_others, stage_oo, N * LO);
+        put(&PtOut::global_state, stage_gs, N * 4);
+        put(&PtOut::obs_self, stage_os, N * 4);
+        if (lane == 0) bulk_commit();
     };
 
     const int T_eff = (p.mode == kPtReset) ? 1 : p.T;
@@ -243,120 +293,179 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         if (p.mode == kPtReset) {
             sel = valid && (p.env_mask == nullptr || p.env_mask[env] != 0);
             if (sel) reset_state((unsigned long long)p.reset_counter);
-            gather_others();
         } else {
-            // ---- action -> control force (environment.py:194-214, core.py:134-140)
-            int act = 0;
+            // ---- actions -> control forces (environment.py:194-214, core.py:134-140)
+            int act[N];
             if (p.actions != nullptr) {
-                act = valid ? (int)p.actions[((size_t)t * B + env) * N + a] : 0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) act[i] = valid ? (int)p.actions[((size_t)t * B + env) * N + i] : 0;
             } else {
                 const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env), (uint64_t)(p.t0 + t));
-                act = action_from_word(philox_word(w, a & 3), 5);
+#pragma unroll
+                for (int i = 0; i < N; ++i) act[i] = action_from_word(philox_word(w, i), 5);
             }
-            if (p.actions_out != nullptr && valid) p.actions_out[((size_t)t * B + env) * N + a] = (int8_t)act;
-            Real fx = (act == 1) ? (Real)-1 : (act == 2) ? (Real)1 : (Real)0;
-            Real fy = (act == 3) ? (Real)-1 : (act == 4) ? (Real)1 : (Real)0;
-            fx = Op::mul(fx, sens); fy = Op::mul(fy, sens);
+            if (p.actions_out != nullptr && valid) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) p.actions_out[((size_t)t * B + env) * N + i] = (int8_t)act[i];
+            }
+            Real fx[N], fy[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const Real ux = (act[i] == 1) ? (Real)-1 : (act[i] == 2) ? (Real)1 : (Real)0;
+                const Real uy = (act[i] == 3) ? (Real)-1 : (act[i] == 4) ? (Real)1 : (Real)0;
+                fx[i] = Op::mul(ux, sens); fy[i] = Op::mul(uy, sens);
+            }
 
-            // ---- contact forces, other agents in index order (core.py:143-155, 180-196).
+            // ---- contact forces over the agent pairs a < b in the reference's order
+            // (core.py:143-155, 180-196; landmarks do not collide, multi-goal_spread.py:55).
             // The reference evaluates the softplus penetration for EVERY pair at every distance;
             // beyond dist_min + ~110 k (float) / ~760 k (double) exp() underflows to exactly 0, so
             // pen == 0, the force is +-0 and "F + p_force" returns p_force bit for bit (p_force is
             // never -0: it starts as +0 or +-sensitivity).  Those pairs are skipped: same bits,
             // none of the double-precision sqrt / div / exp / log1p instructions.
-            if (N > 1) {
+            // All squared distances first (independent arithmetic), then ONE branch for the warp's
+            // common case "no pair anywhere near contact".
+            constexpr int NPAIR = N * (N - 1) / 2;
+            if (NPAIR > 0) {
+                Real d2c[NPAIR > 0 ? NPAIR : 1];
+                bool any_near = false;
+                int q = 0;
 #pragma unroll
-                for (int k = 0; k < NO; ++k) {
-                    const Real qx = __shfl_sync(kFullMask, px, src[k]), qy = __shfl_sync(kFullMask, py, src[k]);
-                    const Real ex = Op::sub(px, qx), ey = Op::sub(py, qy);
-                    const Real d2 = Op::add(Op::mul(ex, ex), Op::mul(ey, ey));
-                    if (!(d2 > far2)) {  // near, coincident or NaN: the literal evaluation
-                        Real dx, dy, dist, x;
-                        Contact<Real>::eval(px, py, qx, qy, p.dist_min, p.contact_margin, dx, dy, dist, x);
-                        const Real pen = Op::mul(logaddexp0<Real>(x), km);
-                        fx = Op::add(Op::mul(Op::div(Op::mul(cf, dx), dist), pen), fx);
-                        fy = Op::add(Op::mul(Op::div(Op::mul(cf, dy), dist), pen), fy);
+                for (int a = 0; a < N; ++a) {
+#pragma unroll
+                    for (int b = a + 1; b < N; ++b) {
+                        const Real ex = Op::sub(px[a], px[b]), ey = Op::sub(py[a], py[b]);
+                        d2c[q] = Op::add(Op::mul(ex, ex), Op::mul(ey, ey));
+                        any_near = any_near || !(d2c[q] > far2);  // near, coincident or NaN
+                        ++q;
+                    }
+                }
+                if (any_near) {
+                    q = 0;
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+#pragma unroll
+                        for (int b = a + 1; b < N; ++b) {
+                            if (!(d2c[q] > far2)) {  // the literal evaluation
+                                const Force2<Real> F = contact_force<Real>(px[a], py[a], px[b], py[b], p.dist_min,
+                                                                           p.contact_margin, cf, km);
+                                fx[a] = Op::add(F.x, fx[a]); fy[a] = Op::add(F.y, fy[a]);    // f_a + p_force[a]
+                                fx[b] = Op::add(-F.x, fx[b]); fy[b] = Op::add(-F.y, fy[b]);  // f_b = -force
+                            }
+                            ++q;
+                        }
                     }
                 }
             }
             // ---- integrate (core.py:158-169)
-            vx = Op::mul(vx, keep); vy = Op::mul(vy, keep);
-            if (!unit_mass) { fx = Op::div(fx, mass); fy = Op::div(fy, mass); }
-            vx = Op::add(vx, Op::mul(fx, dt)); vy = Op::add(vy, Op::mul(fy, dt));
-            px = Op::add(px, Op::mul(vx, dt)); py = Op::add(py, Op::mul(vy, dt));
-            steps += 1;  // environment.py:93
-            gather_others();
-
-            // ---- reward (multi-goal_spread.py:121-138)
-            const Real tx = Op::sub(px, lx), ty = Op::sub(py, ly);
-            Real rew = Op::sub((Real)0, Op::sqrt(Op::add(Op::mul(tx, tx), Op::mul(ty, ty))));
-            const bool my_reached = rew >= neg_reach;
-            int hits = 0;
-            if (N > 1) {
 #pragma unroll
-                for (int k = 0; k < NO; ++k) {
-                    const Real dx = Op::sub(opx[k], px), dy = Op::sub(opy[k], py);
-                    const Real d2 = Op::add(Op::mul(dx, dx), Op::mul(dy, dy));
-                    // sqrt is monotonic: d2 > near2 = (1.01 dist_min)^2 cannot round below dist_min
-                    if (!(d2 > near2)) {
-                        if (Op::sqrt(d2) < dist_min) { rew = Op::sub(rew, (Real)1); hits += 1; }
+            for (int i = 0; i < N; ++i) {
+                if (!unit_mass) { fx[i] = Op::div(fx[i], mass); fy[i] = Op::div(fy[i], mass); }
+                vx[i] = Op::mul(vx[i], keep); vy[i] = Op::mul(vy[i], keep);
+                vx[i] = Op::add(vx[i], Op::mul(fx[i], dt)); vy[i] = Op::add(vy[i], Op::mul(fy[i], dt));
+                px[i] = Op::add(px[i], Op::mul(vx[i], dt)); py[i] = Op::add(py[i], Op::mul(vy[i], dt));
+            }
+            steps += 1;  // environment.py:93
+
+            // ---- rewards (multi-goal_spread.py:121-138)
+            Real rew[N];
+            uint32_t reach_bits = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const Real tx = Op::sub(px[i], lx[i]), ty = Op::sub(py[i], ly[i]);
+                rew[i] = Op::sub((Real)0, Op::sqrt(Op::add(Op::mul(tx, tx), Op::mul(ty, ty))));
+                reach_bits |= (rew[i] >= neg_reach ? 1u : 0u) << i;  // :126-129
+            }
+            int hits = 0;
+            if (NPAIR > 0) {
+                Real d2r[NPAIR > 0 ? NPAIR : 1];
+                bool any_close = false;
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+#pragma unroll
+                    for (int b = a + 1; b < N; ++b) {
+                        const Real dx = Op::sub(px[a], px[b]), dy = Op::sub(py[a], py[b]);
+                        d2r[q] = Op::add(Op::mul(dx, dx), Op::mul(dy, dy));
+                        // sqrt is monotonic: d2 > near2 = (1.01 dist_min)^2 cannot round below dist_min
+                        any_close = any_close || !(d2r[q] > near2);
+                        ++q;
+                    }
+                }
+                if (any_close) {
+                    q = 0;
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+#pragma unroll
+                        for (int b = a + 1; b < N; ++b) {
+                            // is_collision, :114-118 - the penalty and the counter hit both agents
+                            if (!(d2r[q] > near2) && Op::sqrt(d2r[q]) < dist_min) {
+                                rew[a] = Op::sub(rew[a], (Real)1); rew[b] = Op::sub(rew[b], (Real)1);
+                                hits += 2;
+                            }
+                            ++q;
+                        }
                     }
                 }
             }
-            // ---- env-level reductions over the NP lanes of my env
-            Real total = 0;
-            int all_hits = 0;
+            Real total = rew[0];
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const Real rj = __shfl_sync(kFullMask, rew, gb + j);
-                total = (j == 0) ? rj : Op::add(total, rj);  // np.sum, environment.py:107
-                if (N > 1) all_hits += __shfl_sync(kFullMask, hits, gb + j);
-            }
-            const uint32_t reach_bits = (__ballot_sync(kFullMask, my_reached) >> gb) & ((1u << N) - 1u);
-            collisions += all_hits;
+            for (int i = 1; i < N; ++i) total = Op::add(total, rew[i]);  // np.sum, environment.py:107
+            collisions += hits;
             reached = reach_bits;
             const bool done = (steps == p.max_steps) || (reach_bits == (1u << N) - 1u);  // environment.py:118
             if (valid) {
                 const size_t orow = (size_t)t * OB + oe0 + env;
                 for (int d = 0; d < p.n_dst; ++d) {
                     const PtOut &o = p.out[d];
-                    if (o.reward_n != nullptr) reinterpret_cast<Real *>(o.reward_n)[orow * N + a] = rew;
-                    if (a == 0) {
-                        if (o.reward != nullptr) reinterpret_cast<Real *>(o.reward)[orow] = total;
-                        if (o.done != nullptr) o.done[orow] = done ? 1 : 0;
+                    if (o.reward_n != nullptr) {
+                        Real *rn = reinterpret_cast<Real *>(o.reward_n) + orow * N;
+                        if (N == 4) {
+                            st4<Real>(rn, rew[0], rew[N > 1 ? 1 : 0], rew[N > 2 ? 2 : 0], rew[N > 3 ? 3 : 0]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) rn[i] = rew[i];
+                        }
                     }
+                    if (o.reward != nullptr) reinterpret_cast<Real *>(o.reward)[orow] = total;
+                    if (o.done != nullptr) o.done[orow] = done ? 1 : 0;
                 }
             }
-            if (p.auto_reset) {
-                if (done) reset_state((unsigned long long)(p.t0 + t + 1));
-                if (__any_sync(kFullMask, done)) gather_others();
-            }
+            if (p.auto_reset && done) reset_state((unsigned long long)(p.t0 + t + 1));
         }
         emit(t);
-        if (sel && a == 0 && p.out[0].done != nullptr) p.out[0].done[oe0 + env] = 0;  // np.any(done_n), environment.py:149
+        if (sel && o0.done != nullptr) o0.done[oe0 + env] = 0;  // np.any(done_n), environment.py:149
     }
 
     if (valid) {
-        st4<Real>(reinterpret_cast<Real *>(p.sv) + ((size_t)env * N + a) * 4, vx, vy, px, py);
-        if (p.mode == kPtReset || p.auto_reset) {  // landmarks only change on a reset
-            Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + a) * 2;
-            lm[0] = lx; lm[1] = ly;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            st4<Real>(reinterpret_cast<Real *>(p.sv) + ((size_t)env * N + i) * 4, vx[i], vy[i], px[i], py[i]);
+            if (p.mode == kPtReset || p.auto_reset) {  // landmarks only change on a reset
+                Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + i) * 2;
+                lm[0] = lx[i]; lm[1] = ly[i];
+            }
         }
-        if (a == 0) {
-            p.steps[env] = steps;
-            p.collisions[env] = collisions;
-            p.reached[env] = (uint8_t)reached;
-        }
+        p.steps[env] = steps;
+        p.collisions[env] = collisions;
+        p.reached[env] = (uint8_t)reached;
     }
+    if (pending && lane == 0) bulk_wait_all();  // shared memory must outlive the async reads
 }
 
 template <int N, typename Real>
 static int launch_pt(const PtParams &p, cudaStream_t stream) {
-    constexpr int NP = (N == 3) ? 4 : N;
-    constexpr int EW = kWarp / NP;
-    const int nwarps = (p.B + EW - 1) / EW;
-    const int nblocks = (nwarps + kPtThreads / kWarp - 1) / (kPtThreads / kWarp);
-    CM3_CUDA(launch_kernel(particle_kernel<N, Real>, nblocks, kPtThreads, 0, stream, pdl_enabled(), p));
+    using Gm = PtGeom<N, Real>;
+    auto kern = particle_kernel<N, Real>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    CM3_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::kSmemBytes));
+        attr_set[dev] = true;
+    }
+    const int nblocks = (p.B + kWarp - 1) / kWarp;
+    CM3_CUDA(launch_kernel(kern, nblocks, kPtThreads, Gm::kSmemBytes, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 

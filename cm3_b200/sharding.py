@@ -131,9 +131,9 @@ class RolloutAllGather(object):
         shapes = self.env.field_shapes()
         layout, off = {}, 0
         for k in self.fields:
-            dt = torch.uint8 if k == "done" else self.env.dtype
+            dt = self.env.field_dtype(k)
             shp = (self.T, self.shard.total_envs) + tuple(shapes[k][1:])
-            nbytes = int(torch.Size(shp).numel()) * torch.empty((), dtype=dt).element_size()
+            nbytes = int(torch.Size(shp).numel()) * dt.itemsize
             layout[k] = (off, shp, dt)
             off += (nbytes + 255) // 256 * 256
         return layout, off
@@ -151,8 +151,8 @@ class RolloutAllGather(object):
         hdl = symm_mem.rendezvous(buf, grp)
         self._buf, self._hdl, self._layout = buf, hdl, layout
         ptrs = [int(p) for p in hdl.buffer_ptrs]
-        self.gathered = {k: buf[off:off + int(torch.Size(shp).numel()) * torch.empty((), dtype=dt).element_size()]
-                         .view(dt).view(shp) for k, (off, shp, dt) in layout.items()}
+        self.gathered = {k: buf[off:off + int(torch.Size(shp).numel()) * dt.itemsize].view(dt).view(shp)
+                         for k, (off, shp, dt) in layout.items()}
         self._dst_ptrs = [{k: ptrs[r] + layout[k][0] for k in self.fields} for r in range(self.shard.world)]
 
     # ------------------------------------------------------------------ API
@@ -172,9 +172,8 @@ class RolloutAllGather(object):
         shapes = self.env.field_shapes()
         per_env = 0
         for k in self.fields:
-            el = 1 if k == "done" else (8 if self.env.dtype == torch.float64 else 4)
             n = 1
             for d in shapes[k][1:]:
                 n *= d
-            per_env += n * el
+            per_env += n * self.env.field_dtype(k).itemsize
         return per_env * self.env.B * self.T * (self.shard.world - 1)

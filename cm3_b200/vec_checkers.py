@@ -23,12 +23,17 @@ class VecCheckers(object):
 
     def __init__(self, num_envs, n_rows=3, n_columns=16, n_obs=2, agents_r=(0, 2),
                  agents_c=(16, 16), n_agents=1, max_steps=50, device="cuda:0",
-                 dtype=torch.float32, env_id_offset=0):
+                 dtype=torch.float32, env_id_offset=0, tile_dtype=None):
         # the reference's own asserts (checkers.py:16-17)
         assert n_rows % 2 == 1
         assert n_columns % 2 == 0
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be torch.float32 or torch.float64")
+        # grid / obs_self_t only hold {-1, 0, +1}: tile_dtype=torch.int8 writes them as bytes
+        tile_dtype = dtype if tile_dtype is None else tile_dtype
+        if tile_dtype not in (dtype, torch.int8):
+            raise ValueError("tile_dtype must be None (= dtype) or torch.int8")
+        self.tile_dtype = tile_dtype
         self.lib = L.load_library()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -55,6 +60,7 @@ class VecCheckers(object):
             cfg.agents_c[i] = int(agents_c[i])
         cfg.num_envs = self.B
         cfg.real = L.REAL_F64 if dtype == torch.float64 else L.REAL_F32
+        cfg.tile = L.TILE_I8 if tile_dtype == torch.int8 and dtype != torch.int8 else L.TILE_REAL
         cfg.device = dev_index
         cfg.env_id_offset = int(env_id_offset)
         self.env_id_offset = int(env_id_offset)
@@ -84,16 +90,23 @@ class VecCheckers(object):
 
     def bytes_per_env_step(self):
         """Algorithmic bytes of one env-step: outputs + state read/write + actions."""
-        el = 8 if self.dtype == torch.float64 else 4
-        out = sum(int(np.prod(s[1:])) for k, s in self.field_shapes().items() if k != "done") * el + 1
+        out = sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
         state = 2 * (8 + 4 * self.N + 4)
         return out + state + self.N
+
+    def field_dtype(self, k):
+        if k == "done":
+            return torch.uint8
+        return self.tile_dtype if k in ("grid", "obs_self_t") else self.dtype
+
+    def out_bytes_per_env_step(self):
+        return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
 
     def alloc_outputs(self, T=None, pinned_host=False):
         lead = () if T is None else (int(T),)
         out = {}
         for k, shp in self.field_shapes().items():
-            dt = torch.uint8 if k == "done" else self.dtype
+            dt = self.field_dtype(k)
             if pinned_host:
                 out[k] = torch.zeros(lead + shp, dtype=dt).pin_memory()
             else:

@@ -94,11 +94,17 @@ class VecParticle(object):
         state = 2 * (4 * N * el) + 2 * N * el + 2 * 4 + 2 * 4 + 2  # sv rw, landmarks r, steps rw, collisions rw, reached rw
         return out + state + N
 
+    def field_dtype(self, k):
+        return torch.uint8 if k == "done" else self.dtype
+
+    def out_bytes_per_env_step(self):
+        return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
+
     def alloc_outputs(self, T=None, pinned_host=False):
         lead = () if T is None else (int(T),)
         out = {}
         for k, shp in self.field_shapes().items():
-            dt = torch.uint8 if k == "done" else self.dtype
+            dt = self.field_dtype(k)
             if pinned_host:
                 out[k] = torch.zeros(lead + shp, dtype=dt).pin_memory()
             else:

@@ -50,6 +50,10 @@ typedef enum {
 } cm3_status;
 
 typedef enum { CM3_REAL_F32 = 0, CM3_REAL_F64 = 1 } cm3_real;
+/* Element type of the two bulky Checkers outputs (grid, obs_self_t), whose values are always in
+ * {-1, 0, +1}: CM3_TILE_REAL writes them as Real like the reference's float arrays, CM3_TILE_I8
+ * as signed bytes - the same numbers in a quarter of the bytes (HBM, NVLink and PCIe traffic). */
+typedef enum { CM3_TILE_REAL = 0, CM3_TILE_I8 = 1 } cm3_tile;
 
 int cm3_abi_version(void);
 const char *cm3_last_error(void);
@@ -68,7 +72,7 @@ typedef struct {
     int32_t num_envs;      /* B on this device */
     int32_t real;          /* cm3_real of the float outputs */
     int32_t device;        /* CUDA ordinal */
-    int32_t reserved;
+    int32_t tile;          /* cm3_tile of grid / obs_self_t (CM3_TILE_I8 needs real == F32) */
     int64_t env_id_offset; /* global id of local env 0 (keys the Philox streams, so results
                               do not depend on how the batch is sharded over GPUs) */
 } cm3_checkers_config;
@@ -87,10 +91,10 @@ typedef struct {
 /* Outputs of reset/step (env/checkers.py:262,291), dense per field.  For rollouts every
  * pointer addresses [T][B][...].  Any pointer may be NULL: that field is not written. */
 typedef struct {
-    void *grid;          /* [B][n_rows][n_columns+1][2]   Real  get_valid_grid  :66-76  */
+    void *grid;          /* [B][n_rows][n_columns+1][2]   Tile  get_valid_grid  :66-76  */
     void *vec;           /* [B][N][4]                      Real  get_global_state :89-93 */
     void *obs_others;    /* [B][N][2*max(N-1,1)]           Real  :143-151 */
-    void *obs_self_t;    /* [B][N][2*n_obs+1][2*n_obs+1][3] Real get_obs :97-109 */
+    void *obs_self_t;    /* [B][N][2*n_obs+1][2*n_obs+1][3] Tile get_obs :97-109 */
     void *obs_self_v;    /* [B][N][4]                      Real  :137-139 */
     void *reward;        /* [B]                            Real  np.sum(local_rewards) :243 */
     void *local_rewards; /* [B][N]                         Real  :232-237 */

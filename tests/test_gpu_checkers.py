@@ -230,3 +230,35 @@ def test_errors():
     env = VecCheckers(4, **CK2)
     with pytest.raises(ValueError):
         env.reset(goals=np.zeros((2, 2)))
+
+
+@pytest.mark.parametrize("B", [16, 1000, 4099])
+def test_int8_tiles_are_the_same_numbers(B):
+    """tile_dtype=int8: grid / obs_self_t as signed bytes - bit-identical values to the float
+    tiles (and hence to the reference), through step, fused rollout and the host-buffer call."""
+    rng = np.random.default_rng(B)
+    T = 40
+    actions = rng.integers(0, 5, size=(T, B, 2)).astype(np.int8)
+    f32 = VecCheckers(B, **CK2)
+    i8 = VecCheckers(B, tile_dtype=torch.int8, **CK2)
+    assert i8.out["grid"].dtype == torch.int8 and i8.out["obs_self_t"].dtype == torch.int8
+    assert i8.bytes_per_env_step() == 204 + 4 * 23 + 1 + 40 + 2 and f32.bytes_per_env_step() == 951
+    a, b = f32.reset(goals=np.eye(2)), i8.reset(goals=np.eye(2))
+    for t in range(T):
+        for f in gu.CHECKERS_FIELDS:
+            want = a[f].to(torch.int8) if f in ("grid", "obs_self_t") else a[f]
+            assert torch.equal(b[f], want), (t, f)
+        a, b = f32.step(actions[t]), i8.step(actions[t])
+    f32.reset(goals=np.eye(2)); i8.reset(goals=np.eye(2))
+    ra = f32.rollout(T, actions=actions, auto_reset=True)
+    rb = i8.rollout(T, actions=actions, auto_reset=True)
+    for f in gu.CHECKERS_FIELDS:
+        want = ra[f].to(torch.int8) if f in ("grid", "obs_self_t") else ra[f]
+        assert torch.equal(rb[f], want), f
+    h = i8.step_host(actions[0])
+    d = f32.step(actions[0])
+    assert h["obs_self_t"].dtype == np.int8
+    for f in gu.CHECKERS_FIELDS:
+        assert np.array_equal(h[f], d[f].cpu().numpy().astype(h[f].dtype)), f
+    with pytest.raises(Exception):
+        VecCheckers(B, dtype=torch.float64, tile_dtype=torch.int8, **CK2)

@@ -1,0 +1,128 @@
+"""GPU: the vectorised episode loop / transition batches (cm3_b200/rollout.py)
+against a per-env replay of the reference's trainer loop (alg/train_offpolicy.py:299-368,
+alg/train_onpolicy.py:282-350) driven on the oracle, and against a NumPy statement of
+process_batch / process_actions (alg/alg_credit.py:406-499, alg/alg_credit_checkers.py:414-477)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cm3_b200 import VecCheckers, VecParticle, presets
+from cm3_b200.rollout import TransitionCollector, numpy_process_actions
+
+pytestmark = pytest.mark.gpu
+
+
+def trainer_loop_checkers(ctor, goal_idx, actions):
+    """One env, the reference's loop: caller-side reset on done, actions_prev zeroed at reset."""
+    T, n = actions.shape
+    env = oracle.OracleCheckers(1, **ctor)
+    obs = {k: v[0].copy() for k, v in env.reset(goal_idx[None]).items()}
+    prev = np.zeros(n, dtype=np.int64)
+    rows = []
+    for t in range(T):
+        out = {k: v[0].copy() for k, v in env.step(actions[t][None]).items()}
+        rows.append(dict(cur=obs, act=actions[t].copy(), prev=prev.copy(), reward=out["reward"],
+                         local=out["local_rewards"], done=bool(out["done"])))
+        prev = actions[t].astype(np.int64)
+        if out["done"]:
+            out_next = {k: v[0].copy() for k, v in env.reset(goal_idx[None]).items()}
+            prev = np.zeros(n, dtype=np.int64)
+        else:
+            out_next = out
+        rows[-1]["next"] = out_next
+        obs = out_next
+    return rows
+
+
+def test_checkers_transitions_match_the_trainer_loop():
+    B, T = 48, 80
+    ctor = dict(presets.CHECKERS["stage2"], max_steps=presets.MAX_STEPS)
+    env = VecCheckers(B, **ctor)
+    col = TransitionCollector(env, seed=7)
+    col.reset(goals=np.eye(2))
+    tr1 = {k: v.clone() for k, v in col.collect(T // 2).items()}           # fused launch, Philox actions
+    tr2 = col.collect(T - T // 2, policy=lambda obs: (obs["vec"][:, :, 0].long() + 3) % 5)  # per-step policy
+    tr = {k: torch.cat([tr1[k], tr2[k]]).cpu().numpy() for k in tr1}
+    assert tr["actions"].shape == (T, B, 2) and tr["obs_self_t_next"].shape == (T, B, 2, 5, 5, 3)
+    for b in (0, 1, 17, B - 1):
+        rows = trainer_loop_checkers(ctor, np.array([0, 1]), tr["actions"][:, b])
+        for t, r in enumerate(rows):
+            assert np.array_equal(tr["actions_prev"][t, b], r["prev"]), (b, t)
+            assert tr["reward"][t, b] == np.float32(r["reward"]) and bool(tr["done"][t, b]) == r["done"]
+            assert np.array_equal(tr["local_rewards"][t, b], r["local"].astype(np.float32))
+            for f in ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v"):
+                assert np.array_equal(tr[f][t, b], r["cur"][f].astype(np.float32)), (f, b, t)
+                assert np.array_equal(tr[f + "_next"][t, b], r["next"][f].astype(np.float32)), (f, b, t)
+            assert np.array_equal(tr["goals"][t, b], np.eye(2))
+    assert tr["done"].sum() >= 2 * B   # episodes of 33 steps: at least two boundaries per env
+
+
+def test_process_batch_layout_checkers_and_particle():
+    B, T, A = 6, 5, 5
+    env = VecCheckers(B, **dict(presets.CHECKERS["stage2"], max_steps=presets.MAX_STEPS))
+    col = TransitionCollector(env, l_action=A)
+    col.reset(goals=np.eye(2))
+    tr = col.collect(T)
+    out = col.process_batch(tr)
+    assert len(out) == 18 and out[0] == T * B                                   # alg_credit_checkers.py:477
+    (n_steps, state_env, state_agents, obs_others, obs_self_t, obs_self_v, ap1, a1, ao1, reward, reward_local,
+     state_env_n, state_agents_n, obs_others_n, obs_self_t_n, obs_self_v_n, done, goals) = out
+    N = 2
+    assert state_env.shape == (n_steps * N, 3, 9, 2) and state_agents.shape == (n_steps, N, 4)
+    assert obs_self_t.shape == (n_steps * N, 5, 5, 3) and obs_others.shape == (n_steps * N, 2)
+    assert reward.shape == (n_steps,) and reward_local.shape == (n_steps * N,) and done.shape == (n_steps * N,)
+    assert goals.shape == (n_steps, N, 2)
+    npy = {k: v.cpu().numpy() for k, v in tr.items()}
+    # row (t, b, n) <-> index (t*B + b)*N + n; global quantities repeated per agent
+    for (t, b, n) in [(0, 0, 0), (2, 3, 1), (T - 1, B - 1, 1)]:
+        r = (t * B + b) * N + n
+        assert np.array_equal(state_env[r].cpu().numpy(), npy["grid"][t, b])
+        assert np.array_equal(state_env_n[r].cpu().numpy(), npy["grid_next"][t, b])
+        assert np.array_equal(obs_self_t_n[r].cpu().numpy(), npy["obs_self_t_next"][t, b, n])
+        assert np.array_equal(obs_self_v[r].cpu().numpy(), npy["obs_self_v"][t, b, n])
+        assert reward_local[r].item() == npy["local_rewards"][t, b, n] and bool(done[r]) == bool(npy["done"][t, b])
+    # one-hot formatting against the per-env NumPy statement, env by env
+    a1 = a1.cpu().numpy().reshape(T, B, N, A)
+    ao1 = ao1.cpu().numpy().reshape(T, B, N, N - 1, A)
+    ap1 = ap1.cpu().numpy().reshape(T, B, N, A)
+    for b in range(B):
+        w1, wo = numpy_process_actions(npy["actions"][:, b], A)
+        assert np.array_equal(a1[:, b].reshape(T * N, A), w1)
+        assert np.array_equal(ao1[:, b].reshape(T * N, N - 1, A), wo)
+        wp, _ = numpy_process_actions(npy["actions_prev"][:, b], A)
+        assert np.array_equal(ap1[:, b].reshape(T * N, A), wp)
+
+    penv = VecParticle(B, 4, presets.PARTICLE["antipodal"], max_steps=presets.MAX_STEPS)
+    pc = TransitionCollector(penv)
+    pc.reset(seed=3)
+    ptr = pc.collect(T)
+    pout = pc.process_batch(ptr)
+    assert len(pout) == 13 and pout[0] == T * B                                 # alg_credit.py:499
+    (n_steps, v_global, p_others, v_local, pa1, pao1, p_reward, p_reward_local, v_global_n, p_others_n, v_local_n,
+     p_done, p_goals) = pout
+    assert v_global.shape == (n_steps, 4, 4) and p_others.shape == (n_steps * 4, 12) and v_local.shape == (n_steps * 4, 4)
+    assert p_reward.shape == (n_steps * 4,) and pao1.shape == (n_steps * 4, 3, 5) and p_goals.shape == (n_steps, 4, 2)
+    lm = np.stack([presets.PARTICLE["antipodal"]["landmarks_x"], presets.PARTICLE["antipodal"]["landmarks_y"]], axis=1)
+    assert np.allclose(p_goals[0].cpu().numpy(), lm)                            # train_onpolicy.py:283-285
+    q = {k: v.cpu().numpy() for k, v in ptr.items()}
+    r = (3 * B + 2) * 4 + 1
+    assert np.array_equal(v_local_n[r].cpu().numpy(), q["obs_self_next"][3, 2, 1])
+    assert p_reward[r].item() == q["reward"][3, 2] and p_reward_local[r].item() == q["reward_n"][3, 2, 1]
+    # next of step t is current of step t+1 (same buffer, shifted view)
+    assert np.array_equal(q["global_state_next"][:-1], q["global_state"][1:])
+
+
+def test_particle_random_goals_are_tracked_per_step():
+    """prob_random = 1: landmarks are redrawn at every in-kernel reset, so goals differ per step."""
+    B, T = 32, 70
+    env = VecParticle(B, 2, presets.PARTICLE["merge"], prob_random=1.0, max_steps=20)
+    col = TransitionCollector(env)
+    col.reset(seed=5)
+    tr = col.collect(T)
+    goals, done = tr["goals"].cpu().numpy(), tr["done"].cpu().numpy().astype(bool)
+    assert goals.shape == (T, B, 2, 2)
+    for b in range(4):
+        for t in range(T - 1):
+            changed = not np.array_equal(goals[t + 1, b], goals[t, b])
+            assert changed == done[t, b], (b, t)

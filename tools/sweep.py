@@ -82,8 +82,7 @@ def main():
             reps = 10
             ms2 = timed(lambda r: env.rollout(T, actions=None, seed=bench.SEED, t0=r * T, auto_reset=True, out=out),
                         reps, world, device)
-            el = 8 if env.dtype == torch.float64 else 4
-            out_b = sum(int(np.prod(s[1:])) for kf, s in env.field_shapes().items() if kf != "done") * el + 1
+            out_b = env.out_bytes_per_env_step()
             fused_bpe = out_b + (bpe - out_b - spec["n"]) / T
             v_fused = world * B * spec["n"] * T * reps / (ms2 * 1e-3)
             gbs_fused = fused_bpe * B * T * reps / (ms2 * 1e-3) / 1e9
