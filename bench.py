@@ -44,6 +44,7 @@ B_PER_GPU = 65536
 SEED = 12341        # alg/config.json:6
 MAX_STEPS = 33      # alg/config.json:61
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+NVLINK_PEER_GBS = 770.0    # B200_PROFILING.md: measured peer copy, per direction per GPU (900 nominal)
 
 
 def workload_spec(name):
@@ -386,15 +387,18 @@ def run_gpu(args):
                               "actions": "Philox4x32-10 on the device, keyed by (seed, global env id, step)",
                               "rollout_all_gather": gather_mode,
                               "l2": "gathered rollout buffer [%d][%d envs] = %.0f MB per GPU (> 126 MB L2 when >= 2 GPUs at the default size)" % (T, world * B, out_b * world * B * T / 1e6)})
-        out["roofline"].update({"kernel": "fused rollout + all-gather (%s)" % gather_mode,
-                                "algorithmic_bytes_per_env_step": out_b + (bpe - out_b - spec["n"]) / T,
-                                "nvlink_bytes_sent_per_gpu_per_step": sent,
-                                "nvlink_gbs_per_gpu": sent / (launch_us * 1e-6) / 1e9 if world > 1 else 0.0,
-                                "note": "bound by NVLink egress (900 GB/s per direction per GPU) once world > 1, not by HBM"})
-        a2 = (out_b + (bpe - out_b - spec["n"]) / T) * (world if gather_mode else 1) * B / (launch_us * 1e-6) / 1e9
-        out["roofline"]["achieved"] = a2  # HBM bytes written on THIS GPU: the whole gathered batch
-        out["roofline"]["frac"] = a2 / peak
-        out["roofline"]["bytes_per_launch"] = (out_b + (bpe - out_b - spec["n"]) / T) * world * B * T
+        hbm_written = (out_b + state_b / T) * world * B / (step_us * 1e-6) / 1e9  # the whole gathered batch lands in this GPU's HBM
+        nv = sent / (step_us * 1e-6) / 1e9 if world > 1 else 0.0
+        out["roofline"] = {"bound": "nvlink" if world > 1 else "hbm", "achieved": nv if world > 1 else hbm_written,
+                           "peak": NVLINK_PEER_GBS if world > 1 else peak, "unit": "GB/s",
+                           "frac": (nv / NVLINK_PEER_GBS) if world > 1 else hbm_written / peak, "traffic": None,
+                           "peak_source": "measured peer-copy reference, B200_PROFILING.md (770 GB/s per direction per GPU; 900 nominal)" if world > 1 else peak_src,
+                           "kernel": "%s rollout_gather (%s)" % (kname, gather_mode),
+                           "nvlink_bytes_sent_per_gpu_per_step": sent, "nvlink_gbs_per_gpu": nv,
+                           "hbm_gbs_written_per_gpu": hbm_written, "hbm_frac": hbm_written / peak,
+                           "algorithmic_bytes_per_env_step": out_b + state_b / T,
+                           "bytes_per_launch": (out_b + state_b / T) * world * B * T, "launch_us": step_us * T,
+                           "note": "every output byte of a shard is delivered to each of the other %d GPU(s): the exchange, not the stepper, bounds this configuration" % (world - 1)}
     if args.gather != "none":
         pass  # the collective run reports the kernel-side number only
     elif rank == 0 and not args.no_extras:
@@ -508,7 +512,9 @@ def run_reference(args):
         return
     import oracle
     spec = workload_spec(args.workload)
-    nthreads = oracle.max_threads()
+    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: not a limit we accept
+    # for the baseline)
+    nthreads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
     Bs = min(args.envs, 16384)
     K, W = args.steps, max(args.warmup, 3)
     env, reset = make_oracle(spec, Bs, nthreads)

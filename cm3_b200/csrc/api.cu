@@ -79,6 +79,16 @@ struct cm3_particle_s {
     PtParams base;
 };
 
+// the kernels read an env's N action bytes as one word (common.cuh: load_actions_packed)
+static int check_actions_alignment(const int8_t *actions, int N) {
+    const uintptr_t need = (N == 4) ? 4 : (N == 2) ? 2 : 1;
+    if (actions && (reinterpret_cast<uintptr_t>(actions) % need) != 0) {
+        set_error("actions must be %d-byte aligned for n_agents=%d", (int)need, N);
+        return CM3_ERR_BAD_ARG;
+    }
+    return CM3_OK;
+}
+
 static CkOut ck_out(const cm3_checkers_outputs &o) {
     return CkOut{(char *)o.grid, (char *)o.vec, (char *)o.obs_others, (char *)o.obs_self_t, (char *)o.obs_self_v,
                  (char *)o.reward, (char *)o.local_rewards, o.done};
@@ -243,6 +253,7 @@ int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const i
     int rc = ck_fill(h, st, outs, p);
     if (rc != CM3_OK) return rc;
     if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions; p.actions_out = actions_out;
     p.seed = seed; p.t0 = t0;
@@ -259,6 +270,7 @@ int cm3_checkers_rollout_gather(cm3_checkers_t h, const cm3_checkers_state *st, 
     if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
     rc = fill_destinations(n_dst, dsts, dst_B, dst_env0, p.B, p.out, p.n_dst, p.out_B, p.out_env0, ck_out);
     if (rc != CM3_OK) return rc;
+    if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions; p.actions_out = actions_out;
     p.seed = seed; p.t0 = t0;
@@ -424,6 +436,7 @@ int cm3_particle_rollout(cm3_particle_t h, const cm3_particle_state *st, const i
     int rc = pt_fill(h, st, outs, p);
     if (rc != CM3_OK) return rc;
     if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
+    if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions; p.actions_out = actions_out; p.seed = seed; p.t0 = t0;
     return pt_launch(h, p, stream);
@@ -439,6 +452,7 @@ int cm3_particle_rollout_gather(cm3_particle_t h, const cm3_particle_state *st, 
     if (T < 1) { set_error("T must be >= 1"); return CM3_ERR_BAD_ARG; }
     rc = fill_destinations(n_dst, dsts, dst_B, dst_env0, p.B, p.out, p.n_dst, p.out_B, p.out_env0, pt_out);
     if (rc != CM3_OK) return rc;
+    if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = T; p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions; p.actions_out = actions_out; p.seed = seed; p.t0 = t0;
     return pt_launch(h, p, stream);

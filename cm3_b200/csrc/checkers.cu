@@ -296,6 +296,8 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     };
 
     const int T_eff = (p.mode == kCkReset) ? 1 : p.T;
+    uint32_t act_word = 0;  // packed actions of my env for the upcoming step (prefetched)
+    if (p.mode != kCkReset && p.actions != nullptr && valid) act_word = load_actions_packed<N>(p.actions + (size_t)env * N);
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
         if (p.mode == kCkReset) {
@@ -313,9 +315,11 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             // ---- actions of all agents of my env
             int act[N];
             if (p.actions != nullptr) {
+                // this step's word was loaded one step ahead; issue the load for the next step now
+                const uint32_t w = act_word;
+                if (valid && t + 1 < p.T) act_word = load_actions_packed<N>(p.actions + ((size_t)(t + 1) * B + env) * N);
 #pragma unroll
-                for (int i = 0; i < N; ++i)
-                    act[i] = valid ? (int)p.actions[((size_t)t * B + env) * N + i] : 0;
+                for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
             } else {
                 const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env),
                                                       (uint64_t)(p.t0 + t));

@@ -77,6 +77,19 @@ __device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int i) {
     return i == 0 ? p.x : i == 1 ? p.y : i == 2 ? p.z : p.w;
 }
 
+// ---------------------------------------------------------------- action stream
+// The N int8 actions of one env ([B][N] rows) as one packed word: a single 1/2/4-byte load for
+// N = 1/2/4 (rows are naturally aligned), three byte loads for N = 3.
+template <int N> __device__ __forceinline__ uint32_t load_actions_packed(const int8_t *row) {
+    if (N == 4) return *reinterpret_cast<const uint32_t *>(row);
+    if (N == 2) return *reinterpret_cast<const uint16_t *>(row);
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) w |= (uint32_t)(uint8_t)row[i] << (8 * i);
+    return w;
+}
+__device__ __forceinline__ int unpack_action(uint32_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
+
 // ---------------------------------------------------------------- TMA bulk store
 // Shared -> global bulk copy (SASS: UBLKCP).  Source and destination 16-byte aligned, size a
 // multiple of 16.  Issued by ONE thread after every writer executed fence_proxy_async() and

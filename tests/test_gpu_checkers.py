@@ -262,3 +262,25 @@ def test_int8_tiles_are_the_same_numbers(B):
         assert np.array_equal(h[f], d[f].cpu().numpy().astype(h[f].dtype)), f
     with pytest.raises(Exception):
         VecCheckers(B, dtype=torch.float64, tile_dtype=torch.int8, **CK2)
+
+
+def test_max_batch_sampled_parity():
+    """The top of the batch sweep (1 048 576 envs, BASELINE configs[4]): a launch that large is
+    still exact - 512 envs sampled across the whole id range replay bit for bit in the oracle -
+    and the last (ragged) tile of a non-multiple batch is handled."""
+    for B in (1 << 20, (1 << 20) - 5):
+        T = 6
+        env = VecCheckers(B, **CK2)
+        env.reset(goals=np.eye(2))
+        ro = env.rollout(T, actions=None, seed=3, record_actions=True, auto_reset=True)
+        idx = np.unique(np.concatenate([np.random.default_rng(1).choice(B, 500, replace=False),
+                                        [0, 1, 15, 16, B - 17, B - 16, B - 2, B - 1]]))
+        acts = ro["actions"][:, idx].cpu().numpy()
+        orc = oracle.OracleCheckers(len(idx), **CK2)
+        orc.reset(np.array([[0, 1]]))
+        for t in range(T):
+            ref = orc.step(acts[t])
+            cmp_fields({f: ro[f][t][idx] for f in gu.CHECKERS_FIELDS}, ref, gu.CHECKERS_FIELDS, np.float32,
+                       "B=%d t=%d" % (B, t))
+        del env, ro
+        torch.cuda.empty_cache()

@@ -257,3 +257,31 @@ def test_step_host_and_masked_reset():
     assert torch.equal(after[~m], before[~m])
     assert torch.all(after[m][:, :, 0:2] == 0)
     assert torch.all(env.state["steps"][m] == 0) and torch.all(env.state["steps"][~m] == 1)
+
+
+def test_max_batch_sampled_parity_f64():
+    """Top of the batch sweep (1 048 576 envs x 4 agents), float64 state: 512 envs sampled across
+    the id range (incl. the first / last tiles of a non-multiple batch) replay in the oracle from
+    the device-drawn initial state with the recorded Philox actions."""
+    N, T = 4, 12
+    cfg4 = presets.PARTICLE["antipodal"]
+    for B in ((1 << 20) - 3,):
+        env = VecParticle(B, N, dict(cfg4, initial_std=0.3), prob_random=0.3, max_steps=presets.MAX_STEPS,
+                          dtype=torch.float64)
+        first = np_of(env.reset(seed=11, reset_counter=0))
+        lm_all = env.state["landmarks"].cpu().numpy()
+        ro = env.rollout(T, actions=None, seed=11, record_actions=True)
+        idx = np.unique(np.concatenate([np.random.default_rng(4).choice(B, 500, replace=False),
+                                        [0, 1, 31, 32, B - 33, B - 32, B - 2, B - 1]]))
+        orc = oracle.OracleParticle(len(idx), N, max_steps=presets.MAX_STEPS)
+        orc.reset_to(first["global_state"][idx][:, :, 2:4], lm_all[idx])
+        acts = ro["actions"][:, idx].cpu().numpy()
+        for t in range(T):
+            ref = orc.step(acts[t])
+            for f in ("global_state", "obs_others", "obs_self", "reward", "reward_n"):
+                np.testing.assert_allclose(ro[f][t][idx].cpu().numpy(), ref[f], rtol=F64_RTOL, atol=F64_ATOL,
+                                           err_msg="t=%d %s" % (t, f))
+            np.testing.assert_array_equal(ro["done"][t][idx].cpu().numpy(), ref["done"])
+        hits = int(orc.get_state()["collisions"].sum())
+        assert hits > 0   # initial_std 0.3 + random placement: some sampled envs are in contact
+        np.testing.assert_array_equal(env.state["collisions"][idx].cpu().numpy(), orc.get_state()["collisions"])
