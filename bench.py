@@ -401,15 +401,14 @@ def run_gpu(args):
                            "note": "every output byte of a shard is delivered to each of the other %d GPU(s): the exchange, not the stepper, bounds this configuration" % (world - 1)}
     if args.gather != "none":
         pass  # the collective run reports the kernel-side number only
-    elif rank == 0 and not args.no_extras:
-        out["e2e"] = measure_e2e(env, spec, args)
-        out["extra"] = measure_extras(env, spec, args, peak, mode, world, device, local_rank, ring)
-        if spec["kind"] == "checkers":
-            out["extra"]["e2e_int8_tiles"] = measure_e2e_int8(spec, args, device)
-        if world == 1:
-            out["cpu_baseline"] = cpu_baseline(spec, args)
-    elif rank == 0:
-        out["e2e"] = measure_e2e(env, spec, args)
+    else:
+        out["e2e"] = measure_e2e(env, spec, args, world)   # all ranks take part
+        if rank == 0 and not args.no_extras:
+            out["extra"] = measure_extras(env, spec, args, peak, mode, world, device, local_rank, ring)
+            if spec["kind"] == "checkers":
+                out["extra"]["e2e_int8_tiles"] = measure_e2e_int8(spec, args, device)
+            if world == 1:
+                out["cpu_baseline"] = cpu_baseline(spec, args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -417,11 +416,13 @@ def run_gpu(args):
         print(json.dumps(out))
 
 
-def measure_e2e(env, spec, args):
+def measure_e2e(env, spec, args, world=1):
     """The same metric through the host-buffer entry point (cm3_*_step_host): each step copies the
     step's actions from pinned host memory to the device, launches the kernel and copies EVERY
-    output field back into pinned host memory, then waits."""
+    output field back into pinned host memory, then waits.  With world > 1 every rank drives its
+    own GPU (own PCIe link) at the same time; the value is the whole job's, from the slowest rank."""
     import torch
+    import torch.distributed as dist
     B, N = env.B, env.N
     rng = np.random.default_rng(SEED)
     acts = rng.integers(0, 5, size=(8, B, N)).astype(np.int8)
@@ -429,13 +430,20 @@ def measure_e2e(env, spec, args):
     for t in range(3):
         env.step_host(acts[t % 8])
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for t in range(steps):
         out = env.step_host(acts[t % 8])
     float(out["reward"][0])
     el = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([el], device=env.device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        el = float(tt.item())
     bo = sum(v.nbytes for v in out.values())
-    return {"value": B * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": int(bo),
+    return {"value": world * B * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": world * B * N,
+            "d2h_bytes_per_step": world * int(bo), "n_gpus": world,
             "steps": steps, "ms_per_step": el * 1e3 / steps,
             "api": "VecCheckers/VecParticle.step_host -> cm3_*_step_host (host actions in, all output fields out, pinned)",
             "note": "no auto-reset on this path (reference semantics); PCIe-bound: %.1f MB D2H per step" % (bo / 1e6)}

@@ -285,3 +285,36 @@ def test_max_batch_sampled_parity_f64():
         hits = int(orc.get_state()["collisions"].sum())
         assert hits > 0   # initial_std 0.3 + random placement: some sampled envs are in contact
         np.testing.assert_array_equal(env.state["collisions"][idx].cpu().numpy(), orc.get_state()["collisions"])
+
+
+@pytest.mark.parametrize("dtype,rtol,atol", [(torch.float64, F64_RTOL, F64_ATOL), (torch.float32, F32_RTOL, F32_ATOL)])
+def test_coincident_agents_propagate_nan_like_the_reference(dtype, rtol, atol):
+    """dist == 0 is unguarded in the reference (core.py:186-194: delta_pos / dist = 0/0): the two
+    coincident agents get NaN forces, positions, rewards and observations; agents that are merely
+    near go through the literal softplus; far ones are untouched.  Same NaN pattern on the device."""
+    N, B = 4, 64
+    cfg = presets.PARTICLE["antipodal"]
+    rng = np.random.default_rng(9)
+    pos = np.tile(np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1), (B, 1, 1)).astype(np.float64)
+    pos = (pos + rng.normal(0, 0.01, pos.shape)).astype(np.float32).astype(np.float64)
+    pos[0::4, 1] = pos[0::4, 0]                       # env 0, 4, 8, ...: agents 0 and 1 coincide
+    pos[1::4, 2] = pos[1::4, 3] + [0.29, 0.0]         # in contact, not coincident
+    pos[2::4, 2] = pos[2::4, 3] + [0.4, 0.0]          # inside the softplus tail, outside collision
+    lm = np.tile(np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1), (B, 1, 1)).astype(np.float64)
+    orc = oracle.OracleParticle(B, N, max_steps=presets.MAX_STEPS)
+    env = VecParticle(B, N, cfg, max_steps=presets.MAX_STEPS, dtype=dtype)
+    orc.reset_to(pos, lm)
+    env.reset(init_pos=pos, init_landmarks=lm)
+    a = rng.integers(0, 5, size=(B, N)).astype(np.int8)
+    with np.errstate(all="ignore"):
+        ref = orc.step(a)
+    out = np_of(env.step(a))
+    assert np.isnan(ref["global_state"][0, 0]).all() and np.isnan(ref["global_state"][0, 1]).all()
+    assert not np.isnan(ref["global_state"][0, 2:]).any() and not np.isnan(ref["global_state"][1:4]).any()
+    for f in ("global_state", "obs_others", "obs_self", "reward", "reward_n"):
+        assert np.array_equal(np.isnan(out[f]), np.isnan(ref[f])), f
+        np.testing.assert_allclose(out[f], ref[f], rtol=rtol, atol=atol, err_msg=f)
+    np.testing.assert_array_equal(out["done"], ref["done"])
+    np.testing.assert_array_equal(env.state["collisions"].cpu().numpy(), orc.get_state()["collisions"])
+    # the pair at 0.29 was pushed apart by the literal contact force (new distance 0.6 - 0.29 +- actions)
+    assert abs(ref["global_state"][1, 2, 2] - ref["global_state"][1, 3, 2]) > 0.29
