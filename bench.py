@@ -523,7 +523,7 @@ def run_reference(args):
     # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: not a limit we accept
     # for the baseline)
     nthreads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
-    Bs = min(args.envs, 16384)
+    Bs = args.envs if args.ref_envs <= 0 else min(args.envs, args.ref_envs)   # default: the FULL batch per step
     K, W = args.steps, max(args.warmup, 3)
     env, reset = make_oracle(spec, Bs, nthreads)
     rng = np.random.default_rng(SEED)
@@ -569,6 +569,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--ref-envs", type=int, default=0,
+                    help="--impl reference: envs per step (0 = the full --envs batch; a smaller sample stays L3-resident)")
     ap.add_argument("--mode", default="fused", choices=["fused", "step"],
                     help="fused: one launch per 33-step episode (headline); step: one launch per step")
     ap.add_argument("--gather", default="none", choices=["none", "nccl", "peer", "auto"],
