@@ -79,6 +79,8 @@ SYMBOLS = {
     "cm3_checkers_step_host": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
                                          C.POINTER(CheckersOutputs), C.POINTER(CheckersOutputs),
                                          _vp]),
+    "cm3_checkers_step_host_packed": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
+                                                C.POINTER(CheckersOutputs), _vp, _vp, C.c_size_t, _vp]),
     "cm3_particle_default_config": (None, [C.POINTER(ParticleConfig), _i32, _i32]),
     "cm3_particle_create": (C.c_int, [C.POINTER(ParticleConfig), C.POINTER(_vp)]),
     "cm3_particle_destroy": (C.c_int, [_vp]),
@@ -94,6 +96,8 @@ SYMBOLS = {
     "cm3_particle_step_host": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp,
                                          C.POINTER(ParticleOutputs), C.POINTER(ParticleOutputs),
                                          _vp]),
+    "cm3_particle_step_host_packed": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp,
+                                                C.POINTER(ParticleOutputs), _vp, _vp, C.c_size_t, _vp]),
 }
 
 _lib = None

@@ -64,7 +64,42 @@ bool pdl_enabled() {
     return on;
 }
 
+bool tma_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_TMA");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
 static size_t real_size(int real) { return real == CM3_REAL_F64 ? 8 : 4; }
+
+// Device-to-host delivery of the output fields of *_step_host: one copy per requested field.
+struct FieldCopy { void *dst; const void *src; size_t bytes; };
+
+static int copy_fields_to_host(const FieldCopy *cp, int n, cudaStream_t s) {
+    for (int i = 0; i < n; ++i) {
+        if (!cp[i].dst) continue;
+        if (!cp[i].src) { set_error("host output requested for a field with no device buffer"); return CM3_ERR_BAD_ARG; }
+        CM3_CUDA(cudaMemcpyAsync(cp[i].dst, cp[i].src, cp[i].bytes, cudaMemcpyDeviceToHost, s));
+    }
+    return CM3_OK;
+}
+
+// *_step_host_packed: every device field must lie inside the caller's block, which then travels
+// as ONE copy (the facades carve the single-step outputs and their pinned mirror out of one
+// allocation each, cm3_b200/_buffers.py).
+static int check_fields_in_block(const FieldCopy *cp, int n, const void *dev_block, size_t block_bytes) {
+    const char *lo = (const char *)dev_block, *hi = lo + block_bytes;
+    for (int i = 0; i < n; ++i) {
+        const char *f = (const char *)cp[i].src;
+        if (f && (f < lo || f + cp[i].bytes > hi)) {
+            set_error("output field %d lies outside [dev_block, dev_block + block_bytes)", i);
+            return CM3_ERR_BAD_ARG;
+        }
+    }
+    return CM3_OK;
+}
 
 }  // namespace cm3
 
@@ -283,10 +318,10 @@ int cm3_checkers_step(cm3_checkers_t h, const cm3_checkers_state *st, const int8
     return cm3_checkers_rollout(h, st, actions, 0, 0, 1, 0, nullptr, outs, stream);
 }
 
-int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
-                           int8_t *actions_dev, const cm3_checkers_outputs *od,
-                           const cm3_checkers_outputs *oh, void *stream) {
-    if (!h || !actions_host || !actions_dev || !od || !oh) {
+static int ck_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
+                        int8_t *actions_dev, const cm3_checkers_outputs *od, const cm3_checkers_outputs *oh,
+                        const void *dev_block, void *host_block, size_t block_bytes, void *stream) {
+    if (!h || !actions_host || !actions_dev || !od || (!oh && !host_block) || (host_block && !dev_block)) {
         set_error("handle/actions/outputs pointer is NULL");
         return CM3_ERR_BAD_ARG;
     }
@@ -296,10 +331,9 @@ int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const
     const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
     const size_t W = 2 * h->cfg.n_obs + 1, L = 2 * (N > 1 ? N - 1 : 1);
     const size_t ts = h->cfg.tile == CM3_TILE_I8 ? 1 : rs;
-    CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
-    int rc = cm3_checkers_step(h, st, actions_dev, od, stream);
-    if (rc != CM3_OK) return rc;
-    struct { void *dst; const void *src; size_t bytes; } cp[] = {
+    static const cm3_checkers_outputs none = {};
+    if (!oh) oh = &none;
+    const FieldCopy cp[] = {
         {oh->grid, od->grid, B * h->cfg.n_rows * (h->cfg.n_columns + 1) * 2 * ts},
         {oh->vec, od->vec, B * N * 4 * rs},
         {oh->obs_others, od->obs_others, B * N * L * rs},
@@ -309,13 +343,29 @@ int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const
         {oh->local_rewards, od->local_rewards, B * N * rs},
         {oh->done, od->done, B},
     };
-    for (auto &c : cp) {
-        if (!c.dst) continue;
-        if (!c.src) { set_error("host output requested for a field with no device buffer"); return CM3_ERR_BAD_ARG; }
-        CM3_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
-    }
+    const int n = (int)(sizeof(cp) / sizeof(cp[0]));
+    int rc;
+    if (host_block && (rc = check_fields_in_block(cp, n, dev_block, block_bytes)) != CM3_OK) return rc;
+    CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
+    if ((rc = cm3_checkers_step(h, st, actions_dev, od, stream)) != CM3_OK) return rc;
+    if (host_block) CM3_CUDA(cudaMemcpyAsync(host_block, dev_block, block_bytes, cudaMemcpyDeviceToHost, s));
+    else if ((rc = copy_fields_to_host(cp, n, s)) != CM3_OK) return rc;
     CM3_CUDA(cudaStreamSynchronize(s));
     return CM3_OK;
+}
+
+int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
+                           int8_t *actions_dev, const cm3_checkers_outputs *od,
+                           const cm3_checkers_outputs *oh, void *stream) {
+    if (!oh) { set_error("handle/actions/outputs pointer is NULL"); return CM3_ERR_BAD_ARG; }
+    return ck_step_host(h, st, actions_host, actions_dev, od, oh, nullptr, nullptr, 0, stream);
+}
+
+int cm3_checkers_step_host_packed(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
+                                  int8_t *actions_dev, const cm3_checkers_outputs *od, const void *dev_block,
+                                  void *host_block, size_t block_bytes, void *stream) {
+    if (!dev_block || !host_block) { set_error("dev_block/host_block is NULL"); return CM3_ERR_BAD_ARG; }
+    return ck_step_host(h, st, actions_host, actions_dev, od, nullptr, dev_block, host_block, block_bytes, stream);
 }
 
 /* ------------------------------------------------------------------ Particle */
@@ -464,10 +514,10 @@ int cm3_particle_step(cm3_particle_t h, const cm3_particle_state *st, const int8
     return cm3_particle_rollout(h, st, actions, 0, 0, 1, 0, nullptr, outs, stream);
 }
 
-int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
-                           int8_t *actions_dev, const cm3_particle_outputs *od,
-                           const cm3_particle_outputs *oh, void *stream) {
-    if (!h || !actions_host || !actions_dev || !od || !oh) {
+static int pt_step_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
+                        int8_t *actions_dev, const cm3_particle_outputs *od, const cm3_particle_outputs *oh,
+                        const void *dev_block, void *host_block, size_t block_bytes, void *stream) {
+    if (!h || !actions_host || !actions_dev || !od || (!oh && !host_block) || (host_block && !dev_block)) {
         set_error("handle/actions/outputs pointer is NULL");
         return CM3_ERR_BAD_ARG;
     }
@@ -476,10 +526,9 @@ int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st, const
     cudaStream_t s = (cudaStream_t)stream;
     const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
     const size_t LO = 4 * (N > 1 ? N - 1 : 1);
-    CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
-    int rc = cm3_particle_step(h, st, actions_dev, od, stream);
-    if (rc != CM3_OK) return rc;
-    struct { void *dst; const void *src; size_t bytes; } cp[] = {
+    static const cm3_particle_outputs none = {};
+    if (!oh) oh = &none;
+    const FieldCopy cp[] = {
         {oh->global_state, od->global_state, B * N * 4 * rs},
         {oh->obs_others, od->obs_others, B * N * LO * rs},
         {oh->obs_self, od->obs_self, B * N * 4 * rs},
@@ -487,13 +536,29 @@ int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st, const
         {oh->reward_n, od->reward_n, B * N * rs},
         {oh->done, od->done, B},
     };
-    for (auto &c : cp) {
-        if (!c.dst) continue;
-        if (!c.src) { set_error("host output requested for a field with no device buffer"); return CM3_ERR_BAD_ARG; }
-        CM3_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s));
-    }
+    const int n = (int)(sizeof(cp) / sizeof(cp[0]));
+    int rc;
+    if (host_block && (rc = check_fields_in_block(cp, n, dev_block, block_bytes)) != CM3_OK) return rc;
+    CM3_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * N, cudaMemcpyHostToDevice, s));
+    if ((rc = cm3_particle_step(h, st, actions_dev, od, stream)) != CM3_OK) return rc;
+    if (host_block) CM3_CUDA(cudaMemcpyAsync(host_block, dev_block, block_bytes, cudaMemcpyDeviceToHost, s));
+    else if ((rc = copy_fields_to_host(cp, n, s)) != CM3_OK) return rc;
     CM3_CUDA(cudaStreamSynchronize(s));
     return CM3_OK;
+}
+
+int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
+                           int8_t *actions_dev, const cm3_particle_outputs *od,
+                           const cm3_particle_outputs *oh, void *stream) {
+    if (!oh) { set_error("handle/actions/outputs pointer is NULL"); return CM3_ERR_BAD_ARG; }
+    return pt_step_host(h, st, actions_host, actions_dev, od, oh, nullptr, nullptr, 0, stream);
+}
+
+int cm3_particle_step_host_packed(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
+                                  int8_t *actions_dev, const cm3_particle_outputs *od, const void *dev_block,
+                                  void *host_block, size_t block_bytes, void *stream) {
+    if (!dev_block || !host_block) { set_error("dev_block/host_block is NULL"); return CM3_ERR_BAD_ARG; }
+    return pt_step_host(h, st, actions_host, actions_dev, od, nullptr, dev_block, host_block, block_bytes, stream);
 }
 
 }  // extern "C"

@@ -37,18 +37,24 @@ namespace cm3 {
 #endif
 constexpr int kCkWarpsPerBlock = CM3_CK_WPB;
 
-template <typename Real> __device__ __forceinline__ Real tri_value(uint32_t nz, uint32_t neg);
-// value in {0, +1, -1}: nz = cell is non-zero, neg = cell is -1 (neg implies nz)
-template <> __device__ __forceinline__ float tri_value<float>(uint32_t nz, uint32_t neg) {
-    return __uint_as_float(nz * 0x3F800000u | (neg << 31));
+// Cells hold a value in {0, +1, -1}, described by two bit masks over the cells of a row: nz (cell
+// is non-zero) and neg (cell is -1; neg implies nz).  tri_pack() puts the two masks side by side,
+// w = nz | neg << 8 (at most 8 cells at a time), and tri_cell<T>(w, j) expands cell j:
+//   float : (w & (0x101 << j)) * (0x3F800000 >> j) - the nz bit lands on 0x3F800000 (1.0f), the neg
+//           bit on 0x7F << 31 = 0x80000000 (mod 2^32, 0x7F is odd), their sum is 0xBF800000 (-1.0f):
+//           one LOP3 and one IMAD per output word, no conversions;
+//   int8  : the same numbers as signed bytes (compact tiles: lossless, 4x fewer bytes);
+//   double: a conversion (parity mode only).
+__device__ __forceinline__ uint32_t tri_pack(uint32_t nz, uint32_t neg) { return (nz & 0xFFu) | ((neg & 0xFFu) << 8); }
+template <typename Tile> __device__ __forceinline__ Tile tri_cell(uint32_t w, int j);
+template <> __device__ __forceinline__ float tri_cell<float>(uint32_t w, int j) {
+    return __uint_as_float((w & (0x101u << j)) * (0x3F800000u >> j));
 }
-template <> __device__ __forceinline__ double tri_value<double>(uint32_t nz, uint32_t neg) {
-    return (double)((int)nz - 2 * (int)neg);
+template <> __device__ __forceinline__ double tri_cell<double>(uint32_t w, int j) {
+    return (double)((int)((w >> j) & 1u) - 2 * (int)((w >> (j + 8)) & 1u));
 }
-
-// compact tiles: the same {-1, 0, +1} as signed bytes (lossless; 4x fewer bytes over HBM / PCIe)
-template <> __device__ __forceinline__ int8_t tri_value<int8_t>(uint32_t nz, uint32_t neg) {
-    return (int8_t)(nz | (neg * 0xFEu));
+template <> __device__ __forceinline__ int8_t tri_cell<int8_t>(uint32_t w, int j) {
+    return (int8_t)(((w >> j) & 1u) | (((w >> (j + 8)) & 1u) * 0xFEu));
 }
 
 template <typename Real> __device__ __forceinline__ void store4(Real *p, Real a, Real b, Real c, Real d);
@@ -89,7 +95,7 @@ struct CkGeom {
     static constexpr int CNT = R * C / 2 + 1;
     static constexpr int kWinBytes = round_up(EW * N * WW3 * (int)sizeof(Tile), 16);
     static constexpr int kGridBytes = round_up(EW * G * (int)sizeof(Tile), 16);
-    static constexpr int kWarpStageBytes = kWinBytes + kGridBytes;
+    static constexpr int kWarpStageBytes = kWinBytes + kGridBytes + ActionStream<N>::kSmemBytes;
     static constexpr int kLutBytes = round_up((TR + TC + CNT) * (int)sizeof(Real), 128);
     static constexpr int kSmemBytes = kLutBytes + kCkWarpsPerBlock * kWarpStageBytes;
     static constexpr uint32_t CM = (C >= 32) ? 0xFFFFFFFFu : ((1u << C) - 1u);
@@ -98,6 +104,7 @@ struct CkGeom {
     static constexpr uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
     static_assert(R % 2 == 1 && C % 2 == 0, "checkers.py:16-17");
     static_assert(R * C <= 64 && TC <= 32 && TR <= kCkMaxTR && N >= 1 && N <= CM3_MAX_AGENTS, "geometry");
+    static_assert(W <= 8, "tri_pack holds 8 cells");
 
     // cells (i,j) with (i+j) even are green, odd orange (checkers.py:54-63)
     static __host__ __device__ constexpr uint64_t color_all(int color) {
@@ -172,6 +179,13 @@ checkers_kernel(const __grid_constant__ CkParams p) {
 
     bool pending = false;  // bulk stores of this warp whose smem source may still be in flight
 
+    // action rows: streamed through shared memory (multi-step launches on whole tiles, see
+    // ActionStream), else loaded directly at the top of each step
+    ActionStream<N> acts;
+    acts.init(reinterpret_cast<unsigned char *>(stage_grid) + Gm::kGridBytes, p.mode == kCkReset ? nullptr : p.actions, p.B,
+              env0, EW, nenv == EW, p.T, lane);
+    uint32_t act_word = acts.on ? acts.begin(e) : 0u;
+
     // Expands the observations of the current state into the outputs of time slot t.
     const CkOut &o0 = p.out[0];
     const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
@@ -181,7 +195,9 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         if (pending) {
             if (lane < 2) bulk_wait_read();
         }
+        if (acts.on) acts.wait();
         __syncwarp();
+        if (acts.on) act_word = acts.advance(t, e);
         // ---------------- window of agent a (get_obs, checkers.py:97-109)
         if (o0.obs_self_t != nullptr && valid) {
             Tile *win = stage_win + (e * N + a) * WW3;
@@ -206,12 +222,13 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 const uint32_t ng1 = ((rowrem & omask) << O) >> sh;
                 const uint32_t nz2 = (border | occ) >> sh;
                 const uint32_t ng2 = occ >> sh;
+                const uint32_t w0 = tri_pack(nz0, ng0), w1 = tri_pack(nz1, ng1), w2 = tri_pack(nz2, ng2);
 #pragma unroll
                 for (int dc = 0; dc < W; ++dc) {
                     Tile *cell = win + (dr * W + dc) * 3;
-                    cell[0] = tri_value<Tile>((nz0 >> dc) & 1u, (ng0 >> dc) & 1u);
-                    cell[1] = tri_value<Tile>((nz1 >> dc) & 1u, (ng1 >> dc) & 1u);
-                    cell[2] = tri_value<Tile>((nz2 >> dc) & 1u, (ng2 >> dc) & 1u);
+                    cell[0] = tri_cell<Tile>(w0, dc);
+                    cell[1] = tri_cell<Tile>(w1, dc);
+                    cell[2] = tri_cell<Tile>(w2, dc);
                 }
             }
         }
@@ -244,11 +261,13 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                     const int mych = (N > 1) ? a : ch;
                     const uint32_t cmask = (((i & 1) ^ mych) ? Gm::kOdd : Gm::kEven);
                     const uint32_t neg = rowrem & cmask;
+                    // columns in groups of 8 (tri_pack); column C (the start column) holds no reward
 #pragma unroll
-                    for (int j = 0; j <= C; ++j) {
-                        const uint32_t nzb = (j < C) ? ((cmask >> j) & 1u) : 0u;
-                        const uint32_t ngb = (j < C) ? ((neg >> j) & 1u) : 0u;
-                        gr[(i * (C + 1) + j) * 2 + mych] = tri_value<Tile>(nzb, ngb);
+                    for (int j0 = 0; j0 <= C; j0 += 8) {
+                        const uint32_t w = tri_pack(cmask >> j0, neg >> j0);
+#pragma unroll
+                        for (int j = j0; j < j0 + 8 && j <= C; ++j)
+                            gr[(i * (C + 1) + j) * 2 + mych] = tri_cell<Tile>(w, j - j0);
                     }
                 }
             }
@@ -296,8 +315,6 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     };
 
     const int T_eff = (p.mode == kCkReset) ? 1 : p.T;
-    uint32_t act_word = 0;  // packed actions of my env for the upcoming step (prefetched)
-    if (p.mode != kCkReset && p.actions != nullptr && valid) act_word = load_actions_packed<N>(p.actions + (size_t)env * N);
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
         if (p.mode == kCkReset) {
@@ -315,9 +332,8 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             // ---- actions of all agents of my env
             int act[N];
             if (p.actions != nullptr) {
-                // this step's word was loaded one step ahead; issue the load for the next step now
-                const uint32_t w = act_word;
-                if (valid && t + 1 < p.T) act_word = load_actions_packed<N>(p.actions + ((size_t)(t + 1) * B + env) * N);
+                uint32_t w = act_word;  // picked up from the stream during the previous emit
+                if (!acts.on && valid) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
 #pragma unroll
                 for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
             } else {
@@ -397,7 +413,8 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             p.agents[(size_t)env * N + i] =
                 (uint32_t)ar[i] | ((uint32_t)ac[i] << 8) | ((uint32_t)ng[i] << 16) | ((uint32_t)no[i] << 24);
     }
-    if (pending && lane < 2) bulk_wait_all();  // smem must outlive the async reads
+    // smem must outlive the async reads; the global writes themselves complete with the grid
+    if (pending && lane < 2) bulk_wait_read();
 }
 
 // ------------------------------------------------------------------------ host side

@@ -1,5 +1,7 @@
 // common.cuh - shared device helpers for the sm_100a env-step kernels.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the driver entry point is looked up at run time)
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -77,6 +79,8 @@ __device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int i) {
     return i == 0 ? p.x : i == 1 ? p.y : i == 2 ? p.z : p.w;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // ---------------------------------------------------------------- action stream
 // The N int8 actions of one env ([B][N] rows) as one packed word: a single 1/2/4-byte load for
 // N = 1/2/4 (rows are naturally aligned), three byte loads for N = 3.
@@ -89,6 +93,78 @@ template <int N> __device__ __forceinline__ uint32_t load_actions_packed(const i
     return w;
 }
 __device__ __forceinline__ int unpack_action(uint32_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
+
+// Multi-step launches stream the action rows of a warp's env tile through shared memory with
+// cp.async (SASS: LDGSTS), two steps ahead, and pick the packed word of the NEXT step up from
+// shared memory inside the emit phase of the current one:
+//  * a register prefetch does not work here: ptxas makes the first use of the CURRENT word wait on
+//    the scoreboard of the load just issued for the NEXT one (ncu, round 1: 27 % of all warp stall
+//    samples on that instruction);
+//  * cp.async.wait_group and cp.async.bulk.wait_group.read are the same SASS (DEPBAR.LE SB0): a
+//    wait for the action rows also waits for the warp's output tiles to drain.  The kernels wait
+//    for that drain anyway right before they overwrite the staging tiles, so that is where the
+//    rows are picked up - at the top of a step the wait stalled the physics behind the previous
+//    step's stores (ncu, round 1: 21 % of the stall samples).
+// The tile's rows of one step are tile_envs * N contiguous bytes of the [T][B][N] int8 array.
+template <int N>
+struct ActionStream {
+    static constexpr int kSlotBytes = 128;            // >= 32 envs * 4 agents
+    static constexpr int kSmemBytes = 2 * kSlotBytes;  // double buffered
+    unsigned char *slots;
+    const int8_t *tile0;  // row of the tile's first env at step 0
+    size_t step_bytes;    // B * N
+    int nwords, lane, T;
+    bool on;
+
+    // on: whole tile, multi-step launch, every step's rows 4-byte aligned; otherwise the caller
+    // falls back to direct loads
+    __device__ __forceinline__ void init(unsigned char *smem, const int8_t *actions, int B, int env0, int tile_envs,
+                                         bool whole_tile, int T_, int lane_) {
+        slots = smem; lane = lane_; T = T_;
+        step_bytes = (size_t)B * N;
+        tile0 = actions + (size_t)env0 * N;
+        nwords = tile_envs * N / 4;
+        on = actions != nullptr && T > 1 && whole_tile && (tile_envs * N) % 4 == 0 &&
+             ((reinterpret_cast<uintptr_t>(tile0) | step_bytes) & 3u) == 0;
+    }
+    // rows of step t -> slot t & 1 (asynchronous)
+    __device__ __forceinline__ void issue(int t) const {
+        if (t < T && lane < nwords) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                         :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "l"(tile0 + (size_t)t * step_bytes + 4 * lane)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // every issued row has landed (all lanes; follow with __syncwarp() before read())
+    __device__ __forceinline__ void wait() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    // packed action word (byte i = agent i) of local env e of the tile at step t
+    __device__ __forceinline__ uint32_t read(int t, int e) const {
+        const unsigned char *row = slots + (t & 1) * kSlotBytes + e * N;
+        if (N == 4) return *reinterpret_cast<const uint32_t *>(row);
+        if (N == 2) return *reinterpret_cast<const uint16_t *>(row);
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) w |= (uint32_t)row[i] << (8 * i);
+        return w;
+    }
+    // launch prologue: rows of steps 0 and 1 in flight, word of step 0 returned
+    __device__ __forceinline__ uint32_t begin(int e) const {
+        issue(0);
+        issue(1);
+        wait();
+        __syncwarp();
+        return read(0, e);
+    }
+    // inside emit(t), after the drain wait and the __syncwarp() that follows it: the word of step
+    // t + 1, and the rows of step t + 2 go in flight into the slot step t just vacated
+    __device__ __forceinline__ uint32_t advance(int t, int e) const {
+        const uint32_t w = (t + 1 < T) ? read(t + 1, e) : 0u;
+        __syncwarp();  // every lane has read slot (t + 1) & 1 ... and slot t & 1 one step ago
+        issue(t + 2);
+        return w;
+    }
+};
 
 // ---------------------------------------------------------------- TMA bulk store
 // Shared -> global bulk copy (SASS: UBLKCP).  Source and destination 16-byte aligned, size a
@@ -110,6 +186,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 // every committed group has fully completed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// TMA tensor store of one box (SASS: UTMASTG): shared tile -> the box at coordinates (c0, c1) of
+// the 2-D tensor described by `tm` (a __grid_constant__ kernel parameter), un-doing the map's
+// swizzle pattern.  Same bulk-group completion mechanism as bulk_store.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *ssrc, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// brings a tensor map into the TMA descriptor cache ahead of its first use
+__device__ __forceinline__ void tma_prefetch_map(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
 __host__ __device__ constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------- programmatic dependent launch
@@ -119,7 +209,11 @@ __host__ __device__ constexpr int round_up(int x, int m) { return (x + m - 1) / 
 // the previous grid has completed and its writes are visible.  Both instructions are no-ops for
 // a launch without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+#ifdef CM3_EXP_NO_PDL_WAIT  // timing experiment only (tools/exp_g.sh): results are racy
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 template <typename P>
 inline cudaError_t launch_kernel(void (*kern)(P), int nblocks, int nthreads, size_t smem, cudaStream_t stream,

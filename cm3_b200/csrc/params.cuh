@@ -1,5 +1,6 @@
 // params.cuh - kernel parameter blocks shared by the kernels and the C-ABI layer.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,6 +56,9 @@ template <typename Real> struct PtConsts {
     Real dt, keep, contact_force, contact_margin, dist_min, mass, sensitivity, neg_reach, far2, near2;
 };
 
+// tensor maps of the three tiled particle outputs (particle.cu: swizzled staging + UTMASTG)
+struct PtTensorMaps { CUtensorMap gs, os, oo; };
+
 struct PtParams {
     char *sv, *landmarks;
     int32_t *steps, *collisions;
@@ -75,6 +79,8 @@ struct PtParams {
     double initial_std, prob_random;
     PtConsts<float> kf;   // the constants above rounded to the kernel's Real on the host
     PtConsts<double> kd;
+    int tma;              // 1: tiles staged swizzled and stored through tm (set by particle_launch)
+    PtTensorMaps tm;
 };
 
 bool checkers_geometry_supported(int R, int C, int O, int N);
@@ -83,6 +89,7 @@ int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaSt
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);
+bool tma_enabled();  // swizzled tiles + tensor-map stores in the particle kernel (CM3_TMA=0 disables)
 bool pdl_enabled();  // programmatic dependent launch between consecutive step launches (CM3_PDL=0 disables)
 
 }  // namespace cm3

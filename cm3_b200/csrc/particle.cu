@@ -16,9 +16,17 @@
 //    65 536-env headline batch is 2048 warps = 14 per SM - one resident wave.  (Round-1's first
 //    version used one lane per (env, agent); ncu showed it latency-bound: 55 warps per SM in 2.3
 //    waves at 80 registers, every pair evaluated twice, 44 shuffles per step.)
-//  * the observation rows are written into a per-warp shared-memory tile whose layout IS the
-//    layout of the output arrays for those 32 envs and leave the SM as one TMA bulk store per
-//    field (cp.async.bulk.global.shared::cta): full-line HBM writes, like the Checkers kernel.
+//  * the observation rows are written into a per-warp shared-memory tile that holds the bytes of
+//    the output arrays for those 32 envs and leaves the SM as one TMA store per field: full-line
+//    HBM writes, like the Checkers kernel.  global_state and obs_self are the same bytes
+//    (environment.py:113-116 vs multi-goal_spread.py:147), so one staged tile feeds both stores.
+//    A thread writes its env's record, so consecutive lanes are a whole record (16 N .. 48 N bytes)
+//    apart - a 4- to 8-way bank conflict per 16-byte store in a linear tile (ncu, round 1: 75 % of
+//    the shared-store wavefronts were conflicts).  The tile is therefore laid out in the TMA
+//    swizzle pattern (32/64/128-byte XOR swizzle chosen per record size, PtGeom::sw_bits) and
+//    stored with cp.async.bulk.tensor through a tensor map (SASS: UTMASTG) that un-swizzles it on
+//    the way out: conflict-free staging, linear global layout.  Ragged batches (B % 32 != 0) and
+//    the multi-destination gather use the linear tile + plain bulk stores (UBLKCP).
 //    Rewards / done flags go straight from registers (consecutive threads -> consecutive words);
 //  * arithmetic follows the reference operation by operation with round-to-nearest intrinsics
 //    (no FMA contraction, IEEE sqrt/div, no fast-math), in float (throughput mode) or double
@@ -158,27 +166,62 @@ __device__ __noinline__ Force2<Real> contact_force(Real ax, Real ay, Real bx, Re
     return Force2<Real>{Op::mul(Op::div(Op::mul(cf, dx), dist), pen), Op::mul(Op::div(Op::mul(cf, dy), dist), pen)};
 }
 
+// 16-byte chunks per env record S = odd * 2^k: lanes one record apart collide on the 8 bank groups
+// unless the 16-byte chunk index is XOR-ed with higher address bits; k = 0 needs no swizzle,
+// k = 1 / 2 / >= 3 the TMA 32- / 64- / 128-byte swizzle (conflict-free for every S, checked
+// exhaustively in tests/test_particle_layout.py).
+__host__ __device__ constexpr int sw_bits_for(int chunks) {
+    return (chunks % 2) ? 0 : (chunks % 4) ? 1 : (chunks % 8) ? 2 : 3;
+}
+__host__ __device__ constexpr int sw_row_bytes(int bits) { return bits ? (16 << bits) : 128; }
+
 template <int N, typename Real>
 struct PtGeom {
     static constexpr int NO = (N > 1) ? N - 1 : 1;  // "other" agents per agent
     static constexpr int LO = 4 * NO;
     static constexpr int kRowBytes = kWarp * N * 4 * (int)sizeof(Real);   // global_state / obs_self tile
     static constexpr int kOthBytes = kWarp * N * LO * (int)sizeof(Real);  // obs_others tile
-    static constexpr int kSmemBytes = 2 * kRowBytes + kOthBytes;
+    static constexpr int kRowSw = sw_bits_for(N * 4 * (int)sizeof(Real) / 16);
+    static constexpr int kOthSw = sw_bits_for(N * LO * (int)sizeof(Real) / 16);
+    static constexpr uint32_t kRowMask = ((1u << kRowSw) - 1u) << 4;  // bits [4, 4+sw) ^= bits [7, 7+sw)
+    static constexpr uint32_t kOthMask = ((1u << kOthSw) - 1u) << 4;
+    static constexpr int kRowW = sw_row_bytes(kRowSw), kOthW = sw_row_bytes(kOthSw);  // tensor-map row widths
+    static constexpr int kRowRows = kRowBytes / kRowW, kOthRows = kOthBytes / kOthW;  // box rows per tile
+    static constexpr int kOthOff = round_up(kRowBytes, 1024);  // swizzle patterns repeat every 1024 bytes
+    static constexpr int kActOff = kOthOff + kOthBytes;             // ActionStream slots
+    static constexpr int kSmemBytes = kActOff + ActionStream<N>::kSmemBytes + 1024;  // + slack to align the tiles
+    static_assert(kRowRows <= 256 && kOthRows <= 256, "TMA box dimension");
 };
 
-template <int N, typename Real>
+// Stores 4 Reals at byte offset `off` of a staging tile laid out in the TMA swizzle pattern
+// `mask` (0 = linear).  The tile base is 1024-byte aligned.
+template <typename Real> __device__ __forceinline__ void stage4(unsigned char *tile, uint32_t off, uint32_t mask,
+                                                                Real a, Real b, Real c, Real d);
+template <> __device__ __forceinline__ void stage4<float>(unsigned char *tile, uint32_t off, uint32_t mask,
+                                                          float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(tile + (off ^ ((off >> 3) & mask))) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void stage4<double>(unsigned char *tile, uint32_t off, uint32_t mask,
+                                                           double a, double b, double c, double d) {
+    const uint32_t o1 = off + 16;
+    *reinterpret_cast<double2 *>(tile + (off ^ ((off >> 3) & mask))) = make_double2(a, b);
+    *reinterpret_cast<double2 *>(tile + (o1 ^ ((o1 >> 3) & mask))) = make_double2(c, d);
+}
+
+// GATHER = false: one destination set (reset / step / rollout); GATHER = true: rollout_gather,
+// every element goes to n_dst destination sets (peer GPUs), linear tiles + plain bulk stores.
+template <int N, typename Real, bool GATHER>
 __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_constant__ PtParams p) {
     using Op = RealOps<Real>;
     using Gm = PtGeom<N, Real>;
     constexpr int NO = Gm::NO, LO = Gm::LO;
+    constexpr uint32_t RS = (uint32_t)sizeof(Real);
 
     pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Real *stage_gs = reinterpret_cast<Real *>(smem_raw);
-    Real *stage_os = reinterpret_cast<Real *>(smem_raw + Gm::kRowBytes);
-    Real *stage_oo = reinterpret_cast<Real *>(smem_raw + 2 * Gm::kRowBytes);
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *stage_row = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char *stage_oo = stage_row + Gm::kOthOff;
 
     const int lane = threadIdx.x;
     const int env0 = blockIdx.x * kWarp;
@@ -194,6 +237,24 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     // squared distances beyond which a pair provably contributes exactly nothing (see below)
     const Real far2 = K.far2, near2 = K.near2;
     const bool unit_mass = (mass == (Real)1);  // x / 1 == x exactly: skip the IEEE division
+
+    // ---- where the outputs go
+    const PtOut &o0 = p.out[0];
+    const bool has_gs = o0.global_state != nullptr, has_os = o0.obs_self != nullptr, has_oo = o0.obs_others != nullptr;
+    const bool tma = !GATHER && p.tma != 0;                     // swizzled tiles + tensor-map stores
+    const uint32_t mask_row = tma ? Gm::kRowMask : 0u, mask_oo = tma ? Gm::kOthMask : 0u;
+    if (tma && threadIdx.x == 0) {
+        if (has_oo) tma_prefetch_map(&p.tm.oo);
+        if (has_gs) tma_prefetch_map(&p.tm.gs);
+        if (has_os) tma_prefetch_map(&p.tm.os);
+    }
+    const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
+    // per-thread output cursors of slot t = 0, advanced by one [out_B] slice per step
+    Real *rn_ptr = reinterpret_cast<Real *>(o0.reward_n) + (oe0 + env) * N;
+    Real *rw_ptr = reinterpret_cast<Real *>(o0.reward) + (oe0 + env);
+    uint8_t *dn_ptr = o0.done + (oe0 + env);
+    int tile_idx = (int)((oe0 + env0) / kWarp);  // tensor-map tile coordinate (tma: out_B, out_env0 % 32 == 0)
+    const int tiles_per_slot = (int)(OB / kWarp);
 
     pdl_wait();  // state written by the previous launch is visible from here on
 
@@ -230,9 +291,13 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         steps = 0; collisions = 0; reached = 0;  // :84-86, :93; environment.py:148
     };
 
-    bool pending = false;  // bulk stores whose shared-memory source may still be in flight
-    const size_t OB = (size_t)p.out_B, oe0 = (size_t)p.out_env0;
-    const PtOut &o0 = p.out[0];
+    bool pending = false;  // async stores whose shared-memory source may still be in flight
+
+    // action rows: streamed through shared memory (multi-step launches on whole tiles, see
+    // ActionStream), else loaded directly at the top of each step
+    ActionStream<N> acts;
+    acts.init(stage_row + Gm::kActOff, p.mode == kPtReset ? nullptr : p.actions, p.B, env0, kWarp, nenv == kWarp, p.T, lane);
+    uint32_t act_word = acts.on ? acts.begin(lane) : 0u;
 
     // observations of the current state -> outputs of slot t (multi-goal_spread.py:145-154,
     // environment.py:113-116)
@@ -240,23 +305,25 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         if (pending) {
             if (lane == 0) bulk_wait_read();
         }
+        if (acts.on) acts.wait();
         __syncwarp();
+        if (acts.on) act_word = acts.advance(t, lane);
         if (valid) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                if (o0.global_state != nullptr) st4<Real>(stage_gs + (lane * N + i) * 4, vx[i], vy[i], px[i], py[i]);
-                if (o0.obs_self != nullptr) st4<Real>(stage_os + (lane * N + i) * 4, vx[i], vy[i], px[i], py[i]);
-                if (o0.obs_others != nullptr) {
-                    Real *oo = stage_oo + (lane * N + i) * LO;
+                // [vel, pos] of agent i: global_state row and obs_self alike
+                if (has_gs || has_os) stage4<Real>(stage_row, (uint32_t)(lane * N + i) * 4u * RS, mask_row, vx[i], vy[i], px[i], py[i]);
+                if (has_oo) {
+                    const uint32_t oo = (uint32_t)(lane * N + i) * (uint32_t)LO * RS;
                     if (N == 1) {  // "others" is the agent itself, :148-153
-                        st4<Real>(oo, Op::sub(vx[0], vx[0]), Op::sub(vy[0], vy[0]), Op::sub(px[0], px[0]),
-                                  Op::sub(py[0], py[0]));
+                        stage4<Real>(stage_oo, oo, mask_oo, Op::sub(vx[0], vx[0]), Op::sub(vy[0], vy[0]),
+                                     Op::sub(px[0], px[0]), Op::sub(py[0], py[0]));
                     } else {
 #pragma unroll
                         for (int k = 0; k < NO; ++k) {
                             const int j = k + (k >= i ? 1 : 0);  // compile-time after unrolling
-                            st4<Real>(oo + 4 * k, Op::sub(vx[j], vx[i]), Op::sub(vy[j], vy[i]), Op::sub(px[j], px[i]),
-                                      Op::sub(py[j], py[i]));
+                            stage4<Real>(stage_oo, oo + 4u * k * RS, mask_oo, Op::sub(vx[j], vx[i]), Op::sub(vy[j], vy[i]),
+                                         Op::sub(px[j], px[i]), Op::sub(py[j], py[i]));
                         }
                     }
                 }
@@ -265,13 +332,27 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         fence_proxy_async();
         __syncwarp();
         pending = false;
+        if (tma) {
+            // whole tiles only (B % 32 == 0): one tensor-map store per field, un-swizzling on the way out
+            if (lane == 0) {
+                const int tile = tile_idx + t * tiles_per_slot;
+                if (has_oo) tma_store_2d(&p.tm.oo, stage_oo, 0, tile * Gm::kOthRows);
+                if (has_gs) tma_store_2d(&p.tm.gs, stage_row, 0, tile * Gm::kRowRows);
+                if (has_os) tma_store_2d(&p.tm.os, stage_row, 0, tile * Gm::kRowRows);
+                bulk_commit();
+            }
+            pending = true;
+            return;
+        }
         const size_t row0 = (size_t)t * OB + oe0 + env0;
-        // one staged tile per field, n_dst bulk stores each: with rollout_gather the destinations
-        // are the rollout buffers of every GPU of the node (peer memory over NVLink)
-        auto put = [&](char *PtOut::*field, const Real *stage, int per_env) {
+        // linear tiles, n_dst bulk stores each: with rollout_gather the destinations are the
+        // rollout buffers of every GPU of the node (peer memory over NVLink)
+        auto put = [&](char *PtOut::*field, const unsigned char *stage_b, int per_env) {
             if (o0.*field == nullptr) return;
+            const Real *stage = reinterpret_cast<const Real *>(stage_b);
             const uint32_t bytes = (uint32_t)(nenv * per_env * sizeof(Real));
-            for (int d = 0; d < p.n_dst; ++d) {
+            const int nd = GATHER ? p.n_dst : 1;
+            for (int d = 0; d < nd; ++d) {
                 Real *g = reinterpret_cast<Real *>(p.out[d].*field) + row0 * (size_t)per_env;
                 if (nenv == kWarp && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
                     if (lane == 0) bulk_store(g, stage, bytes);
@@ -282,14 +363,12 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             }
         };
         put(&PtOut::obs_others, stage_oo, N * LO);
-        put(&PtOut::global_state, stage_gs, N * 4);
-        put(&PtOut::obs_self, stage_os, N * 4);
+        put(&PtOut::global_state, stage_row, N * 4);
+        put(&PtOut::obs_self, stage_row, N * 4);
         if (lane == 0) bulk_commit();
     };
 
     const int T_eff = (p.mode == kPtReset) ? 1 : p.T;
-    uint32_t act_word = 0;  // packed actions of my env for the upcoming step (prefetched)
-    if (p.mode != kPtReset && p.actions != nullptr && valid) act_word = load_actions_packed<N>(p.actions + (size_t)env * N);
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
         if (p.mode == kPtReset) {
@@ -299,9 +378,8 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             // ---- actions -> control forces (environment.py:194-214, core.py:134-140)
             int act[N];
             if (p.actions != nullptr) {
-                // this step's word was loaded one step ahead; issue the load for the next step now
-                const uint32_t w = act_word;
-                if (valid && t + 1 < p.T) act_word = load_actions_packed<N>(p.actions + ((size_t)(t + 1) * B + env) * N);
+                uint32_t w = act_word;  // picked up from the stream during the previous emit
+                if (!acts.on && valid) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
 #pragma unroll
                 for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
             } else {
@@ -420,11 +498,17 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             reached = reach_bits;
             const bool done = (steps == p.max_steps) || (reach_bits == (1u << N) - 1u);  // environment.py:118
             if (valid) {
-                const size_t orow = (size_t)t * OB + oe0 + env;
-                for (int d = 0; d < p.n_dst; ++d) {
-                    const PtOut &o = p.out[d];
-                    if (o.reward_n != nullptr) {
-                        Real *rn = reinterpret_cast<Real *>(o.reward_n) + orow * N;
+                const int nd = GATHER ? p.n_dst : 1;
+                for (int d = 0; d < nd; ++d) {
+                    // destination d: same cursors, rebased from set 0 to set d (GATHER only)
+                    Real *rn = rn_ptr, *rw = rw_ptr;
+                    uint8_t *dn = dn_ptr;
+                    if (GATHER && d > 0) {
+                        rn = reinterpret_cast<Real *>(p.out[d].reward_n + (reinterpret_cast<char *>(rn_ptr) - o0.reward_n));
+                        rw = reinterpret_cast<Real *>(p.out[d].reward + (reinterpret_cast<char *>(rw_ptr) - o0.reward));
+                        dn = p.out[d].done + (dn_ptr - o0.done);
+                    }
+                    if (o0.reward_n != nullptr) {
                         if (N == 4) {
                             st4<Real>(rn, rew[0], rew[N > 1 ? 1 : 0], rew[N > 2 ? 2 : 0], rew[N > 3 ? 3 : 0]);
                         } else {
@@ -432,10 +516,11 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
                             for (int i = 0; i < N; ++i) rn[i] = rew[i];
                         }
                     }
-                    if (o.reward != nullptr) reinterpret_cast<Real *>(o.reward)[orow] = total;
-                    if (o.done != nullptr) o.done[orow] = done ? 1 : 0;
+                    if (o0.reward != nullptr) *rw = total;
+                    if (o0.done != nullptr) *dn = done ? 1 : 0;
                 }
             }
+            rn_ptr += OB * N; rw_ptr += OB; dn_ptr += OB;
             if (p.auto_reset && done) reset_state((unsigned long long)(p.t0 + t + 1));
         }
         emit(t);
@@ -455,13 +540,42 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         p.collisions[env] = collisions;
         p.reached[env] = (uint8_t)reached;
     }
-    if (pending && lane == 0) bulk_wait_all();  // shared memory must outlive the async reads
+    // shared memory must outlive the async reads; the global writes themselves complete with the grid
+    if (pending && lane == 0) bulk_wait_read();
 }
 
-template <int N, typename Real>
-static int launch_pt(const PtParams &p, cudaStream_t stream) {
+// ------------------------------------------------------------------------ host side
+
+// A [T][out_B] output field seen as a 2-D byte tensor of `width`-byte rows; one box = the tile of
+// 32 consecutive envs.  The swizzle mode is the one the kernel staged the tile in.
+static bool encode_tile_map(CUtensorMap *tm, void *base, size_t total_bytes, int sw_bits, int width, int box_rows) {
+    static const PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }();
+    if (!encode || (reinterpret_cast<uintptr_t>(base) & 15u) != 0 || total_bytes % (size_t)width != 0) return false;
+    const cuuint64_t rows = total_bytes / (size_t)width;
+    if (rows == 0 || rows > 0x7FFFFFFFull) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)width, rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)width};
+    const cuuint32_t box[2] = {(cuuint32_t)width, (cuuint32_t)box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUtensorMapSwizzle sw = sw_bits == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : sw_bits == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : sw_bits == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int N, typename Real, bool GATHER>
+static int launch_pt(const PtParams &p0, cudaStream_t stream) {
     using Gm = PtGeom<N, Real>;
-    auto kern = particle_kernel<N, Real>;
+    auto kern = particle_kernel<N, Real, GATHER>;
     static bool attr_set[64] = {};
     int dev = 0;
     CM3_CUDA(cudaGetDevice(&dev));
@@ -469,15 +583,30 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
         CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::kSmemBytes));
         attr_set[dev] = true;
     }
+    PtParams p = p0;
+    p.tma = 0;
+    if (!GATHER && tma_enabled() && p.B % kWarp == 0 && p.out_B % kWarp == 0 && p.out_env0 % kWarp == 0) {
+        // whole tiles everywhere: swizzled staging + tensor-map stores
+        const int T = (p.mode == kPtReset) ? 1 : p.T;
+        const size_t envs = (size_t)T * (size_t)p.out_B;
+        const PtOut &o = p.out[0];
+        bool ok = true;
+        if (o.global_state) ok = ok && encode_tile_map(&p.tm.gs, o.global_state, envs * N * 4 * sizeof(Real), Gm::kRowSw, Gm::kRowW, Gm::kRowRows);
+        if (o.obs_self) ok = ok && encode_tile_map(&p.tm.os, o.obs_self, envs * N * 4 * sizeof(Real), Gm::kRowSw, Gm::kRowW, Gm::kRowRows);
+        if (o.obs_others) ok = ok && encode_tile_map(&p.tm.oo, o.obs_others, envs * N * Gm::LO * sizeof(Real), Gm::kOthSw, Gm::kOthW, Gm::kOthRows);
+        p.tma = ok ? 1 : 0;
+    }
     const int nblocks = (p.B + kWarp - 1) / kWarp;
     CM3_CUDA(launch_kernel(kern, nblocks, kPtThreads, Gm::kSmemBytes, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream) {
-#define CASE(n)                                                        \
-    case n:                                                            \
-        return real == CM3_REAL_F64 ? launch_pt<n, double>(p, stream) : launch_pt<n, float>(p, stream);
+    const bool gather = p.n_dst > 1;
+#define CASE(n)                                                                                              \
+    case n:                                                                                                  \
+        if (gather) return real == CM3_REAL_F64 ? launch_pt<n, double, true>(p, stream) : launch_pt<n, float, true>(p, stream); \
+        return real == CM3_REAL_F64 ? launch_pt<n, double, false>(p, stream) : launch_pt<n, float, false>(p, stream);
     switch (N) {
         CASE(1) CASE(2) CASE(3) CASE(4)
         default: break;

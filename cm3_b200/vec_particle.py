@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from ._buffers import alloc_fields, _to_int8_host
 
 FIELDS = L.ParticleOutputs.FIELDS
 OBS_FIELDS = ("global_state", "obs_others", "obs_self")
@@ -101,15 +102,12 @@ class VecParticle(object):
         return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
 
     def alloc_outputs(self, T=None, pinned_host=False):
+        """Zeroed output buffers: [B, ...] per field (T=None) or [T, B, ...] rollout buffers.  The
+        single-step set of a batch that is a multiple of 32 envs is one packed allocation (every
+        field stays 16-byte aligned), so that step_host needs a single device-to-host copy."""
         lead = () if T is None else (int(T),)
-        out = {}
-        for k, shp in self.field_shapes().items():
-            dt = self.field_dtype(k)
-            if pinned_host:
-                out[k] = torch.zeros(lead + shp, dtype=dt).pin_memory()
-            else:
-                out[k] = torch.zeros(lead + shp, dtype=dt, device=self.device)
-        return out
+        return alloc_fields(self.field_shapes(), self.field_dtype, lead, device=self.device,
+                            pinned=pinned_host, packed=T is None and self.B % 32 == 0)
 
     @staticmethod
     def _outputs_struct(out):
@@ -207,12 +205,23 @@ class VecParticle(object):
         self._keep = (a, arr)
 
     def step_host(self, actions, fields=FIELDS):
+        """Host-buffer step: actions is a host int8 array [B,N]; the requested output fields are
+        copied back into pinned host buffers and returned as NumPy views.  When every field is
+        requested and the single-step buffers are packed (alloc_outputs), the outputs travel as one
+        device-to-host copy (cm3_particle_step_host_packed)."""
         if self._host is None:
             self._host = self.alloc_outputs(pinned_host=True)
             self._host_actions = torch.zeros(self.B, self.N, dtype=torch.int8).pin_memory()
-        self._host_actions.numpy()[...] = np.clip(np.asarray(actions), -128, 127).astype(np.int8).reshape(self.B, self.N)
-        oh = L.ParticleOutputs(*[_ptr(self._host[f]) if f in fields else None for f in FIELDS])
-        L.check(self.lib.cm3_particle_step_host(self._h, C.byref(self._st), _ptr(self._host_actions),
+        self._host_actions.numpy()[...] = _to_int8_host(actions, (self.B, self.N))
+        dev_block, host_block = getattr(self.out, "block", None), getattr(self._host, "block", None)
+        if dev_block is not None and host_block is not None and tuple(fields) == tuple(FIELDS):
+            L.check(self.lib.cm3_particle_step_host_packed(self._h, C.byref(self._st), _ptr(self._host_actions),
+                                                       _ptr(self._actions_dev), C.byref(self._out_c),
+                                                       _ptr(dev_block), _ptr(host_block), dev_block.numel(),
+                                                       self._stream()))
+        else:
+            oh = L.ParticleOutputs(*[_ptr(self._host[f]) if f in fields else None for f in FIELDS])
+            L.check(self.lib.cm3_particle_step_host(self._h, C.byref(self._st), _ptr(self._host_actions),
                                                 _ptr(self._actions_dev), C.byref(self._out_c),
                                                 C.byref(oh), self._stream()))
         return {f: self._host[f].numpy() for f in fields}

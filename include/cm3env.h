@@ -158,6 +158,16 @@ int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st,
                            const cm3_checkers_outputs *outs_dev,
                            const cm3_checkers_outputs *outs_host, void *stream);
 
+/* step_host for a caller that keeps every field of outs_dev inside ONE device allocation
+ * [dev_block, dev_block + block_bytes) and wants the same bytes, at the same offsets, in
+ * host_block: the outputs travel as one device-to-host copy instead of one per field (the call is
+ * PCIe-bound; per-copy set-up time is pure overhead).  Fields of outs_dev outside the block are
+ * rejected with CM3_ERR_BAD_ARG. */
+int cm3_checkers_step_host_packed(cm3_checkers_t h, const cm3_checkers_state *st,
+                                  const int8_t *actions_host, int8_t *actions_dev,
+                                  const cm3_checkers_outputs *outs_dev, const void *dev_block,
+                                  void *host_block, size_t block_bytes, void *stream);
+
 /* ------------------------------------------------------------------ Particle */
 
 /* World / scenario constants (defaults = the reference's, filled by
@@ -244,6 +254,12 @@ int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st,
                            const int8_t *actions_host, int8_t *actions_dev,
                            const cm3_particle_outputs *outs_dev,
                            const cm3_particle_outputs *outs_host, void *stream);
+
+/* see cm3_checkers_step_host_packed */
+int cm3_particle_step_host_packed(cm3_particle_t h, const cm3_particle_state *st,
+                                  const int8_t *actions_host, int8_t *actions_dev,
+                                  const cm3_particle_outputs *outs_dev, const void *dev_block,
+                                  void *host_block, size_t block_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -186,6 +186,42 @@ def test_step_host_matches_device_step():
         cmp_fields(got, orc.step(a), gu.CHECKERS_FIELDS, np.float32, "host t=%d" % t)
 
 
+@pytest.mark.parametrize("tile", [None, torch.int8])
+def test_step_host_packed_is_one_copy_of_the_same_bytes(tile):
+    """Batches that are a multiple of 32 envs keep the single-step outputs in one allocation and
+    bring them back with cm3_checkers_step_host_packed; the result equals the per-field path and
+    the oracle.  A device field outside the block is rejected."""
+    import ctypes as C
+    from cm3_b200 import _lib as L
+    B = 320
+    rng = np.random.default_rng(6)
+    env = VecCheckers(B, tile_dtype=tile, **CK2)
+    assert env.out.block is not None
+    orc = oracle.OracleCheckers(B, **CK2)
+    env.reset(goals=np.eye(2))
+    orc.reset(np.array([[0, 1]]))
+    for t in range(4):
+        a = rng.integers(0, 5, size=(B, 2)).astype(np.int8)
+        sd = env.state_dict()
+        packed = {k: v.copy() for k, v in env.step_host(a).items()}
+        assert env._host.block is not None
+        env.load_state_dict(sd)
+        some = env.step_host(a, fields=("grid", "reward", "done"))  # per-field copies
+        ref = orc.step(a)
+        for f in gu.CHECKERS_FIELDS:
+            want = ref[f].astype(packed[f].dtype) if f != "done" else ref[f]
+            np.testing.assert_array_equal(packed[f], want, err_msg="packed %s t=%d" % (f, t))
+        for f in some:
+            np.testing.assert_array_equal(some[f], packed[f], err_msg=f)
+    other = torch.zeros(B, dtype=torch.float32, device=env.device)  # a reward buffer outside the block
+    oc = L.CheckersOutputs(*[C.c_void_p((other if f == "reward" else env.out[f]).data_ptr()) for f in L.CheckersOutputs.FIELDS])
+    rc = env.lib.cm3_checkers_step_host_packed(env._h, C.byref(env._st), C.c_void_p(env._host_actions.data_ptr()),
+                                               C.c_void_p(env._actions_dev.data_ptr()), C.byref(oc),
+                                               C.c_void_p(env.out.block.data_ptr()), C.c_void_p(env._host.block.data_ptr()),
+                                               env.out.block.numel(), env._stream())
+    assert rc == -1 and b"outside" in env.lib.cm3_last_error()
+
+
 def test_headline_size_properties():
     """BASELINE config 2 at full size (65 536 envs x 2 agents, max_steps 33): size-independent
     invariants - cells only ever get collected, counts equal collected cells, rewards sum up,
