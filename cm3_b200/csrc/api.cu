@@ -64,6 +64,14 @@ bool pdl_enabled() {
     return on;
 }
 
+bool full_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_PT_FULL");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
 bool tma_enabled() {
     static const bool on = [] {
         const char *v = getenv("CM3_TMA");

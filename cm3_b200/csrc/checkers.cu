@@ -241,7 +241,11 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             for (int d = 0; d < p.n_dst; ++d) {
                 Tile *g = reinterpret_cast<Tile *>(p.out[d].obs_self_t) + (slot + env0) * (size_t)(N * WW3);
                 if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
+#ifdef CM3_L2_HINT_BULK
+                    if (lane == 0) bulk_store_hint(g, stage_win, bytes, l2_policy_evict_first());
+#else
                     if (lane == 0) bulk_store(g, stage_win, bytes);
+#endif
                     pending = true;
                 } else {
                     for (int idx = lane; idx < nenv * N * WW3; idx += kWarp) g[idx] = stage_win[idx];
@@ -279,7 +283,11 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             for (int d = 0; d < p.n_dst; ++d) {
                 Tile *g = reinterpret_cast<Tile *>(p.out[d].grid) + (slot + env0) * (size_t)G;
                 if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
+#ifdef CM3_L2_HINT_BULK
+                    if (lane == 1) bulk_store_hint(g, stage_grid, bytes, l2_policy_evict_first());
+#else
                     if (lane == 1) bulk_store(g, stage_grid, bytes);
+#endif
                     pending = true;
                 } else {
                     for (int idx = lane; idx < nenv * G; idx += kWarp) g[idx] = stage_grid[idx];

@@ -79,6 +79,22 @@ __device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int i) {
     return i == 0 ? p.x : i == 1 ? p.y : i == 2 ? p.z : p.w;
 }
 
+// ---------------------------------------------------------------- L2 cache policies
+// The kernels write a long, write-once output stream and re-read a small action stream.  Build
+// experiments (tools/ab_variants.py): with CM3_L2_HINT_BULK / _TMA the stream stores carry an
+// evict-first policy, with CM3_L2_HINT_ACT the action loads an evict-last one, so that the outputs
+// do not push the actions (or the compact state) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---------------------------------------------------------------- action stream
@@ -130,9 +146,16 @@ struct ActionStream {
     // rows of step t -> slot t & 1 (asynchronous)
     __device__ __forceinline__ void issue(int t) const {
         if (t < T && lane < nwords) {
+#ifdef CM3_L2_HINT_ACT
+            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;"
+                         :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "l"(tile0 + (size_t)t * step_bytes + 4 * lane),
+                            "l"(l2_policy_evict_last())
+                         : "memory");
+#else
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                          :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "l"(tile0 + (size_t)t * step_bytes + 4 * lane)
                          : "memory");
+#endif
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -178,6 +201,11 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_store_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the smem source of every committed group has been read (safe to overwrite the staging tile)
 __device__ __forceinline__ void bulk_wait_read() {
@@ -192,6 +220,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *ssrc, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *tm, const void *ssrc, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1), "l"(pol)
                  : "memory");
 }
 

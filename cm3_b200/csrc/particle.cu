@@ -38,7 +38,6 @@
 
 namespace cm3 {
 
-constexpr int kPtThreads = 32;  // one warp per block
 
 template <typename Real> struct Vec4;
 template <> struct Vec4<float> { using type = float4; };
@@ -171,7 +170,11 @@ __device__ __noinline__ Force2<Real> contact_force(Real ax, Real ay, Real bx, Re
 // k = 1 / 2 / >= 3 the TMA 32- / 64- / 128-byte swizzle (conflict-free for every S, checked
 // exhaustively in tests/test_particle_layout.py).
 __host__ __device__ constexpr int sw_bits_for(int chunks) {
+#ifdef CM3_EXP_WIDE_SWIZZLE  // experiment: 128-byte tensor rows wherever a swizzle is needed at all
+    return (chunks % 2) ? 0 : 3;
+#else
     return (chunks % 2) ? 0 : (chunks % 4) ? 1 : (chunks % 8) ? 2 : 3;
+#endif
 }
 __host__ __device__ constexpr int sw_row_bytes(int bits) { return bits ? (16 << bits) : 128; }
 
@@ -210,8 +213,21 @@ template <> __device__ __forceinline__ void stage4<double>(unsigned char *tile, 
 
 // GATHER = false: one destination set (reset / step / rollout); GATHER = true: rollout_gather,
 // every element goes to n_dst destination sets (peer GPUs), linear tiles + plain bulk stores.
-template <int N, typename Real, bool GATHER>
-__global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_constant__ PtParams p) {
+//
+// FULL = true: the common case compiled without its run-time checks - every output field
+// requested, every tile whole (B % 32 == 0), unit mass, tensor-map stores.  The kernel is bound by
+// the latency of a warp's dependent instruction chain (3.5 warps per scheduler at the 65 536-env
+// batch), so the ~25 uniform branches per step that the general kernel spends on optional outputs
+// and ragged tiles are worth removing (ncu, round 1: 13 % of the stall samples were branch
+// resolution and instruction fetch).
+//
+// Measured and dropped (profiles/r01m): a warp-specialised variant - a physics warp handing the
+// (vel, pos) records of each step to an emitter warp through shared memory and named barriers - was
+// 20-40 % SLOWER at 65 536 envs: two warps per tile cap the kernel at 72 registers for a single
+// resident wave, and the physics warp lost more to spills and serialisation than the emitter took
+// off its chain.
+template <int N, typename Real, bool GATHER, bool FULL>
+__global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constant__ PtParams p) {
     using Op = RealOps<Real>;
     using Gm = PtGeom<N, Real>;
     constexpr int NO = Gm::NO, LO = Gm::LO;
@@ -224,10 +240,11 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     unsigned char *stage_oo = stage_row + Gm::kOthOff;
 
     const int lane = threadIdx.x;
+    const bool reset_mode = !FULL && p.mode == kPtReset;
     const int env0 = blockIdx.x * kWarp;
     const int env = env0 + lane;
-    const int nenv = min(kWarp, p.B - env0);
-    const bool valid = lane < nenv;
+    const int nenv = FULL ? kWarp : min(kWarp, p.B - env0);
+    const bool valid = FULL || lane < nenv;
     const size_t B = (size_t)p.B;
 
     // world constants, rounded to Real once on the host (no per-thread F2F conversions)
@@ -236,12 +253,14 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     const Real mass = K.mass, sens = K.sensitivity, neg_reach = K.neg_reach;
     // squared distances beyond which a pair provably contributes exactly nothing (see below)
     const Real far2 = K.far2, near2 = K.near2;
-    const bool unit_mass = (mass == (Real)1);  // x / 1 == x exactly: skip the IEEE division
+    const bool unit_mass = FULL || (mass == (Real)1);  // x / 1 == x exactly: skip the IEEE division
 
     // ---- where the outputs go
     const PtOut &o0 = p.out[0];
-    const bool has_gs = o0.global_state != nullptr, has_os = o0.obs_self != nullptr, has_oo = o0.obs_others != nullptr;
-    const bool tma = !GATHER && p.tma != 0;                     // swizzled tiles + tensor-map stores
+    const bool has_gs = FULL || o0.global_state != nullptr, has_os = FULL || o0.obs_self != nullptr;
+    const bool has_oo = FULL || o0.obs_others != nullptr;
+    const bool has_rn = FULL || o0.reward_n != nullptr, has_rw = FULL || o0.reward != nullptr, has_dn = FULL || o0.done != nullptr;
+    const bool tma = FULL || (!GATHER && p.tma != 0);           // swizzled tiles + tensor-map stores
     const uint32_t mask_row = tma ? Gm::kRowMask : 0u, mask_oo = tma ? Gm::kOthMask : 0u;
     if (tma && threadIdx.x == 0) {
         if (has_oo) tma_prefetch_map(&p.tm.oo);
@@ -279,7 +298,7 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     auto reset_state = [&](unsigned long long counter) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (p.init_pos != nullptr && p.mode == kPtReset) {
+            if (reset_mode && p.init_pos != nullptr) {
                 ld2<Real>(reinterpret_cast<const Real *>(p.init_pos) + ((size_t)env * N + i) * 2, px[i], py[i]);
                 ld2<Real>(reinterpret_cast<const Real *>(p.init_landmarks) + ((size_t)env * N + i) * 2, lx[i], ly[i]);
             } else {
@@ -296,7 +315,7 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
     // action rows: streamed through shared memory (multi-step launches on whole tiles, see
     // ActionStream), else loaded directly at the top of each step
     ActionStream<N> acts;
-    acts.init(stage_row + Gm::kActOff, p.mode == kPtReset ? nullptr : p.actions, p.B, env0, kWarp, nenv == kWarp, p.T, lane);
+    acts.init(stage_row + Gm::kActOff, reset_mode ? nullptr : p.actions, p.B, env0, kWarp, nenv == kWarp, p.T, lane);
     uint32_t act_word = acts.on ? acts.begin(lane) : 0u;
 
     // observations of the current state -> outputs of slot t (multi-goal_spread.py:145-154,
@@ -336,9 +355,16 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
             // whole tiles only (B % 32 == 0): one tensor-map store per field, un-swizzling on the way out
             if (lane == 0) {
                 const int tile = tile_idx + t * tiles_per_slot;
+#ifdef CM3_L2_HINT_TMA
+                const uint64_t pol = l2_policy_evict_first();
+                if (has_oo) tma_store_2d_hint(&p.tm.oo, stage_oo, 0, tile * Gm::kOthRows, pol);
+                if (has_gs) tma_store_2d_hint(&p.tm.gs, stage_row, 0, tile * Gm::kRowRows, pol);
+                if (has_os) tma_store_2d_hint(&p.tm.os, stage_row, 0, tile * Gm::kRowRows, pol);
+#else
                 if (has_oo) tma_store_2d(&p.tm.oo, stage_oo, 0, tile * Gm::kOthRows);
                 if (has_gs) tma_store_2d(&p.tm.gs, stage_row, 0, tile * Gm::kRowRows);
                 if (has_os) tma_store_2d(&p.tm.os, stage_row, 0, tile * Gm::kRowRows);
+#endif
                 bulk_commit();
             }
             pending = true;
@@ -368,10 +394,10 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
         if (lane == 0) bulk_commit();
     };
 
-    const int T_eff = (p.mode == kPtReset) ? 1 : p.T;
+    const int T_eff = reset_mode ? 1 : p.T;
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
-        if (p.mode == kPtReset) {
+        if (reset_mode) {
             sel = valid && (p.env_mask == nullptr || p.env_mask[env] != 0);
             if (sel) reset_state((unsigned long long)p.reset_counter);
         } else {
@@ -508,7 +534,7 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
                         rw = reinterpret_cast<Real *>(p.out[d].reward + (reinterpret_cast<char *>(rw_ptr) - o0.reward));
                         dn = p.out[d].done + (dn_ptr - o0.done);
                     }
-                    if (o0.reward_n != nullptr) {
+                    if (has_rn) {
                         if (N == 4) {
                             st4<Real>(rn, rew[0], rew[N > 1 ? 1 : 0], rew[N > 2 ? 2 : 0], rew[N > 3 ? 3 : 0]);
                         } else {
@@ -516,8 +542,8 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
                             for (int i = 0; i < N; ++i) rn[i] = rew[i];
                         }
                     }
-                    if (o0.reward != nullptr) *rw = total;
-                    if (o0.done != nullptr) *dn = done ? 1 : 0;
+                    if (has_rw) *rw = total;
+                    if (has_dn) *dn = done ? 1 : 0;
                 }
             }
             rn_ptr += OB * N; rw_ptr += OB; dn_ptr += OB;
@@ -531,7 +557,7 @@ __global__ void __launch_bounds__(kPtThreads) particle_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             st4<Real>(reinterpret_cast<Real *>(p.sv) + ((size_t)env * N + i) * 4, vx[i], vy[i], px[i], py[i]);
-            if (p.mode == kPtReset || p.auto_reset) {  // landmarks only change on a reset
+            if (reset_mode || p.auto_reset) {  // landmarks only change on a reset
                 Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + i) * 2;
                 lm[0] = lx[i]; lm[1] = ly[i];
             }
@@ -572,21 +598,29 @@ static bool encode_tile_map(CUtensorMap *tm, void *base, size_t total_bytes, int
                   sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, typename Real, bool GATHER>
-static int launch_pt(const PtParams &p0, cudaStream_t stream) {
+template <int N, typename Real, bool GATHER, bool FULL>
+static int launch_pt(const PtParams &p, cudaStream_t stream) {
     using Gm = PtGeom<N, Real>;
-    auto kern = particle_kernel<N, Real, GATHER>;
+    auto kern = particle_kernel<N, Real, GATHER, FULL>;
+    constexpr int kSmem = Gm::kSmemBytes;
     static bool attr_set[64] = {};
     int dev = 0;
     CM3_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::kSmemBytes));
+        CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set[dev] = true;
     }
-    PtParams p = p0;
+    const int nblocks = (p.B + kWarp - 1) / kWarp;
+    CM3_CUDA(launch_kernel(kern, nblocks, kWarp, kSmem, stream, pdl_enabled(), p));
+    return CM3_OK;
+}
+
+// tensor maps for a single-destination launch over whole tiles; p.tma says whether they were made
+template <int N, typename Real>
+static void make_tensor_maps(PtParams &p) {
+    using Gm = PtGeom<N, Real>;
     p.tma = 0;
-    if (!GATHER && tma_enabled() && p.B % kWarp == 0 && p.out_B % kWarp == 0 && p.out_env0 % kWarp == 0) {
-        // whole tiles everywhere: swizzled staging + tensor-map stores
+    if (p.n_dst == 1 && tma_enabled() && p.B % kWarp == 0 && p.out_B % kWarp == 0 && p.out_env0 % kWarp == 0) {
         const int T = (p.mode == kPtReset) ? 1 : p.T;
         const size_t envs = (size_t)T * (size_t)p.out_B;
         const PtOut &o = p.out[0];
@@ -596,17 +630,23 @@ static int launch_pt(const PtParams &p0, cudaStream_t stream) {
         if (o.obs_others) ok = ok && encode_tile_map(&p.tm.oo, o.obs_others, envs * N * Gm::LO * sizeof(Real), Gm::kOthSw, Gm::kOthW, Gm::kOthRows);
         p.tma = ok ? 1 : 0;
     }
-    const int nblocks = (p.B + kWarp - 1) / kWarp;
-    CM3_CUDA(launch_kernel(kern, nblocks, kPtThreads, Gm::kSmemBytes, stream, pdl_enabled(), p));
-    return CM3_OK;
+}
+
+template <int N, typename Real>
+static int dispatch_pt(const PtParams &p0, cudaStream_t stream) {
+    if (p0.n_dst > 1) return launch_pt<N, Real, true, false>(p0, stream);
+    PtParams p = p0;
+    make_tensor_maps<N, Real>(p);
+    const PtOut &o = p.out[0];
+    // FULL: the step / rollout launch with nothing optional left to test at run time
+    const bool full = p.tma && p.mode == kPtStep && p.mass == 1.0 && o.global_state && o.obs_self && o.obs_others &&
+                      o.reward && o.reward_n && o.done && full_enabled();
+    return full ? launch_pt<N, Real, false, true>(p, stream) : launch_pt<N, Real, false, false>(p, stream);
 }
 
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream) {
-    const bool gather = p.n_dst > 1;
-#define CASE(n)                                                                                              \
-    case n:                                                                                                  \
-        if (gather) return real == CM3_REAL_F64 ? launch_pt<n, double, true>(p, stream) : launch_pt<n, float, true>(p, stream); \
-        return real == CM3_REAL_F64 ? launch_pt<n, double, false>(p, stream) : launch_pt<n, float, false>(p, stream);
+#define CASE(n) \
+    case n: return real == CM3_REAL_F64 ? dispatch_pt<n, double>(p, stream) : dispatch_pt<n, float>(p, stream);
     switch (N) {
         CASE(1) CASE(2) CASE(3) CASE(4)
         default: break;
