@@ -80,10 +80,13 @@ __device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int i) {
 }
 
 // ---------------------------------------------------------------- L2 cache policies
-// The kernels write a long, write-once output stream and re-read a small action stream.  Build
-// experiments (tools/ab_variants.py): with CM3_L2_HINT_BULK / _TMA the stream stores carry an
-// evict-first policy, with CM3_L2_HINT_ACT the action loads an evict-last one, so that the outputs
-// do not push the actions (or the compact state) out of the 126 MB L2.
+// The kernels write a long, write-once output stream and re-read a small action stream and the
+// compact state.  The particle kernel's tensor-map stores carry an evict-first policy so that the
+// outputs do not push the actions out of the 126 MB L2 (measured, profiles/r01o_ab.txt: +5-7 % at
+// 65 536 envs with actions from HBM).  The same hint on the Checkers kernel's plain bulk stores
+// measured 2 % slower and is off (CM3_L2_HINT_BULK builds it); an evict-last hint on the cp.async
+// action loads (cp.async...L2::cache_hint) raised an illegal-instruction fault on sm_100a, so the
+// action rows get an evict-last L2 prefetch instead (ActionStream::issue).
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -146,16 +149,14 @@ struct ActionStream {
     // rows of step t -> slot t & 1 (asynchronous)
     __device__ __forceinline__ void issue(int t) const {
         if (t < T && lane < nwords) {
-#ifdef CM3_L2_HINT_ACT
-            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;"
-                         :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "l"(tile0 + (size_t)t * step_bytes + 4 * lane),
-                            "l"(l2_policy_evict_last())
-                         : "memory");
-#else
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                          :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "l"(tile0 + (size_t)t * step_bytes + 4 * lane)
                          : "memory");
-#endif
+            // ... and the rows of step t + 2 are pulled into L2 with evict-last priority (one request per
+            // 32-byte sector): without it the output stream evicts the action stream and every row
+            // comes from HBM in between the writes (profiles/r01o_ab.txt: +2-4 % of the roofline)
+            if (t + 2 < T && (lane & 7) == 0)
+                asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(tile0 + (size_t)(t + 2) * step_bytes + 4 * lane));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
             // whole tiles only (B % 32 == 0): one tensor-map store per field, un-swizzling on the way out
             if (lane == 0) {
                 const int tile = tile_idx + t * tiles_per_slot;
-#ifdef CM3_L2_HINT_TMA
+#ifndef CM3_NO_L2_HINT_TMA  // write-once stream: evict-first (see common.cuh, L2 cache policies)
                 const uint64_t pol = l2_policy_evict_first();
                 if (has_oo) tma_store_2d_hint(&p.tm.oo, stage_oo, 0, tile * Gm::kOthRows, pol);
                 if (has_gs) tma_store_2d_hint(&p.tm.gs, stage_row, 0, tile * Gm::kRowRows, pol);
