@@ -28,8 +28,7 @@ for g in nccl peer; do
       > gpurun_out/gather_pm2_${g}_n${NG}_$TAG.json 2> gpurun_out/gather_pm2_${g}_n${NG}_$TAG.err; echo "gather pm2 $g n=$NG rc=$?"; tail -2 gpurun_out/gather_pm2_${g}_n${NG}_$TAG.err | cut -c1-300
   summ gpurun_out/gather_pm2_${g}_n${NG}_$TAG.json
 done
-timeout 300 $TR --nproc-per-node $NG --master-port 29511 bench.py --gpus $NG --cpu-seconds 2 > gpurun_out/scale_ck2_n${NG}_$TAG.json 2> gpurun_out/scale_ck2_n${NG}_$TAG.err; echo "scale ck2 n=$NG rc=$?"; tail -2 gpurun_out/scale_ck2_n${NG}_$TAG.err | cut -c1-300
+# one weak-scaling line of the headline (the driver measures 1/2/4/8 itself at round end)
+timeout 300 $TR --nproc-per-node $NG --master-port 29511 bench.py --gpus $NG --no-extras > gpurun_out/scale_ck2_n${NG}_$TAG.json 2> gpurun_out/scale_ck2_n${NG}_$TAG.err; echo "scale ck2 n=$NG rc=$?"; tail -2 gpurun_out/scale_ck2_n${NG}_$TAG.err | cut -c1-300
 summ gpurun_out/scale_ck2_n${NG}_$TAG.json
-timeout 300 $TR --nproc-per-node $NG --master-port 29512 bench.py --gpus $NG --workload pa3 --no-extras > gpurun_out/scale_pa3_n${NG}_$TAG.json 2> gpurun_out/scale_pa3_n${NG}_$TAG.err; echo "scale pa3 n=$NG rc=$?"
-summ gpurun_out/scale_pa3_n${NG}_$TAG.json
 nvidia-smi topo -m > gpurun_out/topo_$TAG.txt 2>&1; head -12 gpurun_out/topo_$TAG.txt; nproc
