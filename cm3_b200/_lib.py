@@ -79,6 +79,8 @@ SYMBOLS = {
     "cm3_checkers_step_host": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
                                          C.POINTER(CheckersOutputs), C.POINTER(CheckersOutputs),
                                          _vp]),
+    "cm3_checkers_get_state": (C.c_int, [_vp, C.POINTER(CheckersState), C.POINTER(CheckersState), _vp]),
+    "cm3_checkers_set_state": (C.c_int, [_vp, C.POINTER(CheckersState), C.POINTER(CheckersState), _vp]),
     "cm3_checkers_step_host_packed": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
                                                 C.POINTER(CheckersOutputs), _vp, _vp, C.c_size_t, _vp]),
     "cm3_particle_default_config": (None, [C.POINTER(ParticleConfig), _i32, _i32]),
@@ -96,6 +98,8 @@ SYMBOLS = {
     "cm3_particle_step_host": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp,
                                          C.POINTER(ParticleOutputs), C.POINTER(ParticleOutputs),
                                          _vp]),
+    "cm3_particle_get_state": (C.c_int, [_vp, C.POINTER(ParticleState), C.POINTER(ParticleState), _vp]),
+    "cm3_particle_set_state": (C.c_int, [_vp, C.POINTER(ParticleState), C.POINTER(ParticleState), _vp]),
     "cm3_particle_step_host_packed": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp,
                                                 C.POINTER(ParticleOutputs), _vp, _vp, C.c_size_t, _vp]),
 }

@@ -376,6 +376,34 @@ int cm3_checkers_step_host_packed(cm3_checkers_t h, const cm3_checkers_state *st
     return ck_step_host(h, st, actions_host, actions_dev, od, nullptr, dev_block, host_block, block_bytes, stream);
 }
 
+static int ck_state_copy(cm3_checkers_t h, const cm3_checkers_state *dev, const cm3_checkers_state *host,
+                         bool to_host, void *stream) {
+    if (!h || !dev || !host || !dev->remaining || !dev->agents || !dev->meta) {
+        set_error("handle/state pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = h->cfg.num_envs, N = h->cfg.n_agents;
+    struct { void *d; void *hst; size_t bytes; } f[] = {
+        {dev->remaining, host->remaining, B * 8}, {dev->agents, host->agents, B * N * 4}, {dev->meta, host->meta, B * 4}};
+    for (auto &c : f) {
+        if (!c.hst) continue;
+        if (to_host) CM3_CUDA(cudaMemcpyAsync(c.hst, c.d, c.bytes, cudaMemcpyDeviceToHost, s));
+        else CM3_CUDA(cudaMemcpyAsync(c.d, c.hst, c.bytes, cudaMemcpyHostToDevice, s));
+    }
+    if (to_host) CM3_CUDA(cudaStreamSynchronize(s));
+    return CM3_OK;
+}
+
+int cm3_checkers_get_state(cm3_checkers_t h, const cm3_checkers_state *dev, const cm3_checkers_state *host, void *stream) {
+    return ck_state_copy(h, dev, host, true, stream);
+}
+int cm3_checkers_set_state(cm3_checkers_t h, const cm3_checkers_state *dev, const cm3_checkers_state *host, void *stream) {
+    return ck_state_copy(h, dev, host, false, stream);
+}
+
 /* ------------------------------------------------------------------ Particle */
 
 void cm3_particle_default_config(cm3_particle_config *cfg, int32_t n_agents, int32_t max_steps) {
@@ -567,6 +595,35 @@ int cm3_particle_step_host_packed(cm3_particle_t h, const cm3_particle_state *st
                                   void *host_block, size_t block_bytes, void *stream) {
     if (!dev_block || !host_block) { set_error("dev_block/host_block is NULL"); return CM3_ERR_BAD_ARG; }
     return pt_step_host(h, st, actions_host, actions_dev, od, nullptr, dev_block, host_block, block_bytes, stream);
+}
+
+static int pt_state_copy(cm3_particle_t h, const cm3_particle_state *dev, const cm3_particle_state *host,
+                         bool to_host, void *stream) {
+    if (!h || !dev || !host || !dev->sv || !dev->landmarks || !dev->steps || !dev->collisions || !dev->reached) {
+        set_error("handle/state pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
+    struct { void *d; void *hst; size_t bytes; } f[] = {
+        {dev->sv, host->sv, B * N * 4 * rs}, {dev->landmarks, host->landmarks, B * N * 2 * rs},
+        {dev->steps, host->steps, B * 4}, {dev->collisions, host->collisions, B * 4}, {dev->reached, host->reached, B}};
+    for (auto &c : f) {
+        if (!c.hst) continue;
+        if (to_host) CM3_CUDA(cudaMemcpyAsync(c.hst, c.d, c.bytes, cudaMemcpyDeviceToHost, s));
+        else CM3_CUDA(cudaMemcpyAsync(c.d, c.hst, c.bytes, cudaMemcpyHostToDevice, s));
+    }
+    if (to_host) CM3_CUDA(cudaStreamSynchronize(s));
+    return CM3_OK;
+}
+
+int cm3_particle_get_state(cm3_particle_t h, const cm3_particle_state *dev, const cm3_particle_state *host, void *stream) {
+    return pt_state_copy(h, dev, host, true, stream);
+}
+int cm3_particle_set_state(cm3_particle_t h, const cm3_particle_state *dev, const cm3_particle_state *host, void *stream) {
+    return pt_state_copy(h, dev, host, false, stream);
 }
 
 }  // extern "C"

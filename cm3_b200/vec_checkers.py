@@ -243,6 +243,22 @@ class VecCheckers(object):
         return {f: self._host[f].numpy() for f in fields}
 
     # ------------------------------------------------------------------ state
+    def get_state_host(self):
+        """NumPy copies of the compact state through cm3_checkers_get_state (checkpointing without a
+        tensor library; state_dict() is the device-side equivalent)."""
+        host = {k: np.empty(tuple(v.shape), dtype=torch.empty(0, dtype=v.dtype).numpy().dtype) for k, v in self.state.items()}
+        hs = L.CheckersState(*[C.c_void_p(host[f].ctypes.data) for f in self.state])
+        L.check(self.lib.cm3_checkers_get_state(self._h, C.byref(self._st), C.byref(hs), self._stream()))
+        return host
+
+    def set_state_host(self, host):
+        """Inverse of get_state_host (cm3_checkers_set_state); missing keys are left untouched."""
+        keep = {k: np.ascontiguousarray(host[k], dtype=torch.empty(0, dtype=self.state[k].dtype).numpy().dtype).reshape(tuple(self.state[k].shape))
+                for k in self.state if k in host}
+        hs = L.CheckersState(*[(C.c_void_p(keep[f].ctypes.data) if f in keep else None) for f in self.state])
+        L.check(self.lib.cm3_checkers_set_state(self._h, C.byref(self._st), C.byref(hs), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # pageable host memory: the arrays may go away
+
     def state_dict(self):
         return {k: v.clone() for k, v in self.state.items()}
 

@@ -158,6 +158,17 @@ int cm3_checkers_step_host(cm3_checkers_t h, const cm3_checkers_state *st,
                            const cm3_checkers_outputs *outs_dev,
                            const cm3_checkers_outputs *outs_host, void *stream);
 
+/* State transfer for bindings without a tensor library (checkpoint / resume, injecting a
+ * reference state for parity): copies the compact state between the caller's device arrays `dev`
+ * and host arrays `host` of the same shapes.  NULL fields of `host` are skipped.  Enqueued on
+ * `stream`; get_state waits for the stream so that the host arrays are filled on return.
+ * The reference keeps no such thing (its state is the Python object itself, env/checkers.py:26-35);
+ * this replaces pickling an env. */
+int cm3_checkers_get_state(cm3_checkers_t h, const cm3_checkers_state *dev, const cm3_checkers_state *host,
+                           void *stream);
+int cm3_checkers_set_state(cm3_checkers_t h, const cm3_checkers_state *dev, const cm3_checkers_state *host,
+                           void *stream);
+
 /* step_host for a caller that keeps every field of outs_dev inside ONE device allocation
  * [dev_block, dev_block + block_bytes) and wants the same bytes, at the same offsets, in
  * host_block: the outputs travel as one device-to-host copy instead of one per field (the call is
@@ -254,6 +265,13 @@ int cm3_particle_step_host(cm3_particle_t h, const cm3_particle_state *st,
                            const int8_t *actions_host, int8_t *actions_dev,
                            const cm3_particle_outputs *outs_dev,
                            const cm3_particle_outputs *outs_host, void *stream);
+
+/* see cm3_checkers_get_state / cm3_checkers_set_state (world.agents[i].state, landmarks, env.steps,
+ * scenario.collisions, agent.reached of the reference objects) */
+int cm3_particle_get_state(cm3_particle_t h, const cm3_particle_state *dev, const cm3_particle_state *host,
+                           void *stream);
+int cm3_particle_set_state(cm3_particle_t h, const cm3_particle_state *dev, const cm3_particle_state *host,
+                           void *stream);
 
 /* see cm3_checkers_step_host_packed */
 int cm3_particle_step_host_packed(cm3_particle_t h, const cm3_particle_state *st,

@@ -173,6 +173,30 @@ def test_masked_reset_and_state_roundtrip():
         assert torch.equal(o1[f], o2[f]), f
 
 
+def test_host_state_roundtrip_through_the_abi():
+    """cm3_checkers_get_state / set_state: a state saved to host arrays and put back reproduces
+    the following steps bit for bit; a partial set leaves the other arrays alone."""
+    B = 500
+    rng = np.random.default_rng(8)
+    env = VecCheckers(B, **CK2)
+    env.reset(goals=np.eye(2))
+    acts = rng.integers(0, 5, size=(6, B, 2)).astype(np.int8)
+    for t in range(3):
+        env.step(acts[t])
+    saved = env.get_state_host()
+    assert saved["remaining"].shape == (B,) and saved["agents"].shape == (B, 2)
+    first = [{k: v.clone() for k, v in env.step(acts[t]).items()} for t in range(3, 6)]
+    env.set_state_host(saved)
+    for t in range(3, 6):
+        out = env.step(acts[t])
+        for f in gu.CHECKERS_FIELDS:
+            assert torch.equal(out[f], first[t - 3][f]), (f, t)
+    meta = env.state["meta"].clone()
+    env.set_state_host({"remaining": saved["remaining"]})
+    assert torch.equal(env.state["meta"], meta)
+    assert np.array_equal(env.get_state_host()["remaining"], saved["remaining"])
+
+
 def test_step_host_matches_device_step():
     B = 300
     rng = np.random.default_rng(5)
