@@ -1,6 +1,7 @@
 """Builds cm3_b200/csrc/libcm3env.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
 import os
 import subprocess
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -43,7 +44,9 @@ def build_library(force=False, verbose=False, defines=(), output=None):
     if not force and not defines and not is_stale():
         return out
     tag = os.path.splitext(os.path.basename(out))[0]
-    objdir = os.path.join(CSRC, "build", tag)
+    # objects live outside the tree (132 MB of -lineinfo objects would travel with every gpurun
+    # snapshot); only the linked library is kept in-tree
+    objdir = os.path.join(os.environ.get("CM3_BUILD_DIR") or os.path.join(tempfile.gettempdir(), "cm3_b200_build"), tag)
     os.makedirs(objdir, exist_ok=True)
     procs, objs = [], []
     for src, unit_defs, name in UNITS:

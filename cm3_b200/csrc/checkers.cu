@@ -192,12 +192,13 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     auto emit = [&](int t) {
         const size_t slot = (size_t)t * OB + oe0;
         const int my_r = pick<N>(ar, a), my_c = pick<N>(ac, a);
+        // next step's action word: in flight from here to the end of this phase (ActionStream)
+        const uint32_t act_loaded = acts.on ? acts.load(t + 1) : 0u;
+        if (acts.on) acts.prefetch(t + 3);
         if (pending) {
             if (lane < 2) bulk_wait_read();
         }
-        if (acts.on) acts.wait();
         __syncwarp();
-        if (acts.on) act_word = acts.advance(t, e);
         // ---------------- window of agent a (get_obs, checkers.py:97-109)
         if (o0.obs_self_t != nullptr && valid) {
             Tile *win = stage_win + (e * N + a) * WW3;
@@ -295,6 +296,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             }
             if (lane == 1) bulk_commit();
         }
+        if (acts.on) act_word = acts.hand_over(t, act_loaded, e);
         // ---------------- small per-agent vectors, straight from registers
         if (valid) {
             const size_t rec = (slot + env) * N + a;

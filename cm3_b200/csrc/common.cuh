@@ -113,17 +113,21 @@ template <int N> __device__ __forceinline__ uint32_t load_actions_packed(const i
 }
 __device__ __forceinline__ int unpack_action(uint32_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
 
-// Multi-step launches stream the action rows of a warp's env tile through shared memory with
-// cp.async (SASS: LDGSTS), two steps ahead, and pick the packed word of the NEXT step up from
-// shared memory inside the emit phase of the current one:
-//  * a register prefetch does not work here: ptxas makes the first use of the CURRENT word wait on
-//    the scoreboard of the load just issued for the NEXT one (ncu, round 1: 27 % of all warp stall
-//    samples on that instruction);
-//  * cp.async.wait_group and cp.async.bulk.wait_group.read are the same SASS (DEPBAR.LE SB0): a
-//    wait for the action rows also waits for the warp's output tiles to drain.  The kernels wait
-//    for that drain anyway right before they overwrite the staging tiles, so that is where the
-//    rows are picked up - at the top of a step the wait stalled the physics behind the previous
-//    step's stores (ncu, round 1: 21 % of the stall samples).
+// Multi-step launches stream the action rows of a warp's env tile through shared memory, one step
+// ahead: at the top of the emit phase of step t every lane loads one 32-bit word of the rows of
+// step t + 1 (they were pulled into L2, evict-last, two steps earlier), the load is in flight while
+// the observation tiles are staged and their stores issued, and at the end of the phase the word is
+// parked in shared memory, from where each thread picks up the packed actions of its own env.
+// What round 1 measured on the way here:
+//  * a register prefetch across the loop back-edge does not work: ptxas makes the first use of the
+//    CURRENT word wait on the scoreboard of the load just issued for the NEXT one (27 % of all warp
+//    stall samples on that instruction, profiles/r01g);
+//  * cp.async (LDGSTS) works but shares its completion scoreboard with the bulk stores
+//    (cp.async.wait_group and cp.async.bulk.wait_group.read are the same DEPBAR.LE SB0), so a
+//    wait for the rows is also a wait for the warp's output tiles - which rules out keeping one
+//    tile in flight while the next is staged (double-buffered staging, particle.cu);
+//  * without the L2 prefetch the output stream evicts the action stream and every row comes from
+//    HBM in between the writes (profiles/r01o_ab.txt: 2-4 % of the roofline).
 // The tile's rows of one step are tile_envs * N contiguous bytes of the [T][B][N] int8 array.
 template <int N>
 struct ActionStream {
@@ -146,47 +150,46 @@ struct ActionStream {
         on = actions != nullptr && T > 1 && whole_tile && (tile_envs * N) % 4 == 0 &&
              ((reinterpret_cast<uintptr_t>(tile0) | step_bytes) & 3u) == 0;
     }
-    // rows of step t -> slot t & 1 (asynchronous)
-    __device__ __forceinline__ void issue(int t) const {
-        if (t < T && lane < nwords) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                         :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "l"(tile0 + (size_t)t * step_bytes + 4 * lane)
-                         : "memory");
-            // ... and the rows of step t + 2 are pulled into L2 with evict-last priority (one request per
-            // 32-byte sector): without it the output stream evicts the action stream and every row
-            // comes from HBM in between the writes (profiles/r01o_ab.txt: +2-4 % of the roofline)
-            if (t + 2 < T && (lane & 7) == 0)
-                asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(tile0 + (size_t)(t + 2) * step_bytes + 4 * lane));
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    // pulls the rows of step t into L2 with evict-last priority (one request per 32-byte sector)
+    __device__ __forceinline__ void prefetch(int t) const {
+        if (t < T && lane < nwords && (lane & 7) == 0)
+            asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(tile0 + (size_t)t * step_bytes + 4 * lane));
     }
-    // every issued row has landed (all lanes; follow with __syncwarp() before read())
-    __device__ __forceinline__ void wait() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    // this lane's word of the rows of step t; volatile so that it stays where it is written (early)
+    __device__ __forceinline__ uint32_t load(int t) const {
+        uint32_t w = 0;
+        if (t < T && lane < nwords)
+            asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(w) : "l"(tile0 + (size_t)t * step_bytes + 4 * lane) : "memory");
+        return w;
+    }
+    // parks the word loaded for step t in slot t & 1 (volatile: stays behind the store issue)
+    __device__ __forceinline__ void stash(int t, uint32_t w) const {
+        if (lane < nwords)
+            asm volatile("st.shared.b32 [%0], %1;" :: "r"(smem_u32(slots + (t & 1) * kSlotBytes + 4 * lane)), "r"(w) : "memory");
+    }
     // packed action word (byte i = agent i) of local env e of the tile at step t
     __device__ __forceinline__ uint32_t read(int t, int e) const {
         const unsigned char *row = slots + (t & 1) * kSlotBytes + e * N;
-        if (N == 4) return *reinterpret_cast<const uint32_t *>(row);
-        if (N == 2) return *reinterpret_cast<const uint16_t *>(row);
+        if (N == 4) return *reinterpret_cast<const volatile uint32_t *>(row);
+        if (N == 2) return *reinterpret_cast<const volatile uint16_t *>(row);
         uint32_t w = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) w |= (uint32_t)row[i] << (8 * i);
+        for (int i = 0; i < N; ++i) w |= (uint32_t)reinterpret_cast<const volatile unsigned char *>(row)[i] << (8 * i);
         return w;
     }
-    // launch prologue: rows of steps 0 and 1 in flight, word of step 0 returned
+    // launch prologue: the word of step 0 (exposed latency, once per launch)
     __device__ __forceinline__ uint32_t begin(int e) const {
-        issue(0);
-        issue(1);
-        wait();
+        prefetch(1);
+        prefetch(2);
+        stash(0, load(0));
         __syncwarp();
         return read(0, e);
     }
-    // inside emit(t), after the drain wait and the __syncwarp() that follows it: the word of step
-    // t + 1, and the rows of step t + 2 go in flight into the slot step t just vacated
-    __device__ __forceinline__ uint32_t advance(int t, int e) const {
-        const uint32_t w = (t + 1 < T) ? read(t + 1, e) : 0u;
-        __syncwarp();  // every lane has read slot (t + 1) & 1 ... and slot t & 1 one step ago
-        issue(t + 2);
-        return w;
+    // end of emit(t): the word loaded at its top becomes the packed actions of step t + 1
+    __device__ __forceinline__ uint32_t hand_over(int t, uint32_t loaded, int e) const {
+        stash(t + 1, loaded);
+        __syncwarp();
+        return read(t + 1, e);
     }
 };
 
@@ -211,6 +214,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // the smem source of every committed group has been read (safe to overwrite the staging tile)
 __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// ... of every committed group but the NEWEST (double-buffered staging: the tile staged one step ago
+// may still be in flight while the other buffer is refilled)
+__device__ __forceinline__ void bulk_wait_read_but_one() {
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 // every committed group has fully completed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

@@ -191,8 +191,16 @@ struct PtGeom {
     static constexpr int kRowW = sw_row_bytes(kRowSw), kOthW = sw_row_bytes(kOthSw);  // tensor-map row widths
     static constexpr int kRowRows = kRowBytes / kRowW, kOthRows = kOthBytes / kOthW;  // box rows per tile
     static constexpr int kOthOff = round_up(kRowBytes, 1024);  // swizzle patterns repeat every 1024 bytes
-    static constexpr int kActOff = kOthOff + kOthBytes;             // ActionStream slots
-    static constexpr int kSmemBytes = kActOff + ActionStream<N>::kSmemBytes + 1024;  // + slack to align the tiles
+    // One staging set = row tile + others tile.  Two sets (double-buffered staging: the stores of
+    // step t drain while step t + 1 is staged into the other set) for N <= 2, where a step is short
+    // compared with the time a store takes to drain: measured +12 % for PM2, -3 % for PA3
+    // (profiles/r01r_ab.txt); PA4's 8 KB sets would not fit twice in the 14 blocks per SM of the
+    // one-wave 65 536-env batch anyway.
+    static constexpr int kSetBytes = round_up(kOthOff + kOthBytes, 1024);
+    static constexpr int kOverhead = ActionStream<N>::kSmemBytes + 1024 /* alignment slack */;
+    static constexpr int kStages = (N <= 2 && 14 * (2 * kSetBytes + kOverhead + 1024 /* driver-reserved */) <= 227 * 1024) ? 2 : 1;
+    static constexpr int kActOff = kStages * kSetBytes;             // ActionStream slots
+    static constexpr int kSmemBytes = kActOff + kOverhead;
     static_assert(kRowRows <= 256 && kOthRows <= 256, "TMA box dimension");
 };
 
@@ -236,8 +244,7 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
     pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *stage_row = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char *stage_oo = stage_row + Gm::kOthOff;
+    unsigned char *stage_base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
     const int lane = threadIdx.x;
     const bool reset_mode = !FULL && p.mode == kPtReset;
@@ -315,18 +322,24 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
     // action rows: streamed through shared memory (multi-step launches on whole tiles, see
     // ActionStream), else loaded directly at the top of each step
     ActionStream<N> acts;
-    acts.init(stage_row + Gm::kActOff, reset_mode ? nullptr : p.actions, p.B, env0, kWarp, nenv == kWarp, p.T, lane);
+    acts.init(stage_base + Gm::kActOff, reset_mode ? nullptr : p.actions, p.B, env0, kWarp, nenv == kWarp, p.T, lane);
     uint32_t act_word = acts.on ? acts.begin(lane) : 0u;
 
     // observations of the current state -> outputs of slot t (multi-goal_spread.py:145-154,
     // environment.py:113-116)
     auto emit = [&](int t) {
+        // next step's action word: in flight from here to the end of this phase (ActionStream)
+        const uint32_t act_loaded = acts.on ? acts.load(t + 1) : 0u;
+        if (acts.on) acts.prefetch(t + 3);
+        // this step's staging set; with two sets only the stores of step t - 2 must have left it
+        unsigned char *stage_row = stage_base + (Gm::kStages == 2 ? (t & 1) * Gm::kSetBytes : 0);
+        unsigned char *stage_oo = stage_row + Gm::kOthOff;
         if (pending) {
-            if (lane == 0) bulk_wait_read();
+            if (lane == 0) {
+                if (Gm::kStages == 2) bulk_wait_read_but_one(); else bulk_wait_read();
+            }
         }
-        if (acts.on) acts.wait();
         __syncwarp();
-        if (acts.on) act_word = acts.advance(t, lane);
         if (valid) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -368,6 +381,7 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
                 bulk_commit();
             }
             pending = true;
+            if (acts.on) act_word = acts.hand_over(t, act_loaded, lane);
             return;
         }
         const size_t row0 = (size_t)t * OB + oe0 + env0;
@@ -392,6 +406,7 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
         put(&PtOut::global_state, stage_row, N * 4);
         put(&PtOut::obs_self, stage_row, N * 4);
         if (lane == 0) bulk_commit();
+        if (acts.on) act_word = acts.hand_over(t, act_loaded, lane);
     };
 
     const int T_eff = reset_mode ? 1 : p.T;
