@@ -252,7 +252,8 @@ __host__ __device__ constexpr int round_up(int x, int m) { return (x + m - 1) / 
 // the previous grid has completed and its writes are visible.  Both instructions are no-ops for
 // a launch without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
-#ifdef CM3_EXP_NO_PDL_WAIT  // timing experiment only (tools/exp_g.sh): results are racy
+#ifdef CM3_EXP_NO_PDL_WAIT  // timing experiment only (racy results): the per-step bound without the
+                            // inter-launch dependency, profiles/r01g_nowait.txt
 __device__ __forceinline__ void pdl_wait() {}
 #else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -1,9 +1,9 @@
 #!/bin/bash
-# GPU experiment E (1 GPU): the round's reference run - parity suite, every bench line, reference
+# 1-GPU reference run of a round - parity suite, every bench line, reference
 # arm, batch sweep, ncu launch lists + full captures (fused and per-step), compute-sanitizer.
 set -u
 mkdir -p gpurun_out
-TAG=${1:-r01e}
+TAG=${1:-r01s}
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu_$TAG.log
 summ() { python - "$1" <<'PY'
 import json,sys
@@ -29,8 +29,8 @@ done
 python bench.py --impl reference --steps 200 > gpurun_out/bench_ref_ck2_$TAG.json 2>&1; python -c "import json; d=json.load(open('gpurun_out/bench_ref_ck2_$TAG.json')); print('ref ck2', d['value'], d['cpu_baseline']['cores'])"
 python bench.py --impl reference --workload pa4 --steps 200 > gpurun_out/bench_ref_pa4_$TAG.json 2>&1; python -c "import json; d=json.load(open('gpurun_out/bench_ref_pa4_$TAG.json')); print('ref pa4', d['value'], d['cpu_baseline']['cores'])"
 python tools/sweep.py --out gpurun_out/sweep_$TAG.jsonl > gpurun_out/sweep_$TAG.log 2>&1; echo "sweep rc=$?"
-for wl in ck2 pa4; do
-  K=checkers_kernel; [ $wl = pa4 ] && K=particle_kernel
+for wl in ck2 pa4 pa3; do
+  K=checkers_kernel; [ $wl != ck2 ] && K=particle_kernel
   # the default (fused) command: launch list + one full capture of the dominant kernel
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${wl}_fused_$TAG.csv \
       python bench.py --workload $wl --steps 330 --warmup 33 --no-extras > gpurun_out/ncu_launch_${wl}_fused_$TAG.log 2>&1; echo "ncu launches fused $wl rc=$?"
@@ -42,7 +42,7 @@ for wl in ck2 pa4; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 20 -c 2 -f -o gpurun_out/prof_${wl}_step_$TAG \
       python bench.py --workload $wl --mode step --steps 66 --warmup 3 --no-extras > gpurun_out/ncu_full_${wl}_step_$TAG.log 2>&1; echo "ncu full step $wl rc=$?"
 done
-SEL="ragged or rollout_equals or masked or auto_reset or int8 or teacher_forced_f32_large"
+SEL="ragged or rollout_equals or masked or auto_reset or int8 or teacher_forced_f32_large or packed"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_checkers.py tests/test_gpu_particle.py -x -q \
     -k "$SEL" > gpurun_out/sanitizer_memcheck_$TAG.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck_$TAG.log
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_checkers.py tests/test_gpu_particle.py -x -q \
