@@ -170,11 +170,9 @@ __device__ __noinline__ Force2<Real> contact_force(Real ax, Real ay, Real bx, Re
 // k = 1 / 2 / >= 3 the TMA 32- / 64- / 128-byte swizzle (conflict-free for every S, checked
 // exhaustively in tests/test_particle_layout.py).
 __host__ __device__ constexpr int sw_bits_for(int chunks) {
-#ifdef CM3_EXP_WIDE_SWIZZLE  // experiment: 128-byte tensor rows wherever a swizzle is needed at all
-    return (chunks % 2) ? 0 : 3;
-#else
+    // (128-byte rows everywhere - fewer, wider TMA rows at the price of 2- to 3-way conflicts for
+    // S = 6, 12 - measured within +-1.5 % of this choice: profiles/r01l_ab.txt, r01w)
     return (chunks % 2) ? 0 : (chunks % 4) ? 1 : (chunks % 8) ? 2 : 3;
-#endif
 }
 __host__ __device__ constexpr int sw_row_bytes(int bits) { return bits ? (16 << bits) : 128; }
 
