@@ -23,9 +23,25 @@ import ref_shims  # noqa: E402
 pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="reference tree not present")
 
 
+def _is_env_module(name):
+    return name in ("multiagent", "env") or name.startswith("multiagent.") or name.startswith("env.")
+
+
 @pytest.fixture(scope="module")
 def ref():
-    return ref_shims.load_reference()
+    """The reference's modules, isolated from the drop-in packages of the same names
+    (cm3_b200/dropin/{env,multiagent}) that other tests may have imported."""
+    saved_modules = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_env_module(k)}
+    saved_path = list(sys.path)
+    sys.path[:] = [p for p in sys.path if "dropin" not in p]
+    try:
+        yield ref_shims.load_reference()
+    finally:
+        for k in list(sys.modules):
+            if _is_env_module(k):
+                del sys.modules[k]
+        sys.modules.update(saved_modules)
+        sys.path[:] = saved_path
 
 
 def replay_checkers(fix):
