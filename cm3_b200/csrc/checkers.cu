@@ -30,8 +30,9 @@
 
 namespace cm3 {
 
-// One warp per block: with 14 KB of staging per warp 16 blocks fit an SM, so the 2048 tiles of the
-// 65 536-env headline batch are resident in a single wave (measured: +7 % over 2 warps per block).
+// One warp per block: with 13 KB of staging per warp 16 blocks fit an SM (ncu: shared-memory limited),
+// i.e. 2368 of the 4096 CK2 tiles of the 65 536-env headline batch are resident at once, 1.73 waves
+// (measured: +7 % over 2 warps per block, profiles/r01b_ab.txt).
 #ifndef CM3_CK_WPB
 #define CM3_CK_WPB 1
 #endif
