@@ -26,22 +26,22 @@
 //    swizzle pattern (32/64/128-byte XOR swizzle chosen per record size, PtGeom::sw_bits) and
 //    stored with cp.async.bulk.tensor through a tensor map (SASS: UTMASTG) that un-swizzles it on
 //    the way out: conflict-free staging, linear global layout.  Ragged batches (B % 32 != 0) and
-//    the multi-destination gather use the linear tile + plain bulk stores (UBLKCP).
+//    the multi-destination gather use the linear tile + plain bulk stores (UBLKCP).  The tensor-map
+//    stores carry an L2 evict-first policy (write-once stream); for N <= 2 the staging set is
+//    double buffered (PtGeom::kStages).
 //    Rewards / done flags go straight from registers (consecutive threads -> consecutive words);
 //  * arithmetic follows the reference operation by operation with round-to-nearest intrinsics
 //    (no FMA contraction, IEEE sqrt/div, no fast-math), in float (throughput mode) or double
 //    (free-running parity mode);
-//  * T steps can be fused in one launch with state in registers, Philox actions and in-kernel
-//    episode reset, like the Checkers kernel.
+//  * T steps can be fused in one launch with state in registers, actions from Philox or streamed
+//    one step ahead through shared memory (common.cuh: ActionStream) and in-kernel episode reset,
+//    like the Checkers kernel;
+//  * the common launch (all outputs, whole tiles, unit mass) has its own instantiation without the
+//    run-time checks of the general one (template parameter FULL).
 #include "common.cuh"
 #include "params.cuh"
 
 namespace cm3 {
-
-
-template <typename Real> struct Vec4;
-template <> struct Vec4<float> { using type = float4; };
-template <> struct Vec4<double> { using type = double4; };
 
 template <typename Real> __device__ __forceinline__ void ld4(const Real *p, Real &a, Real &b, Real &c, Real &d);
 template <> __device__ __forceinline__ void ld4<float>(const float *p, float &a, float &b, float &c, float &d) {
