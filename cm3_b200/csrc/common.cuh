@@ -86,7 +86,7 @@ __device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int i) {
 // 65 536 envs with actions from HBM).  The same hint on the Checkers kernel's plain bulk stores
 // measured 2 % slower and is off (CM3_L2_HINT_BULK builds it); an evict-last hint on the cp.async
 // action loads (cp.async...L2::cache_hint) raised an illegal-instruction fault on sm_100a, so the
-// action rows get an evict-last L2 prefetch instead (ActionStream::issue).
+// action rows get an evict-last L2 prefetch instead (ActionStream::prefetch).
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -121,7 +121,7 @@ __device__ __forceinline__ int unpack_action(uint32_t w, int i) { return (int)(i
 // What round 1 measured on the way here:
 //  * a register prefetch across the loop back-edge does not work: ptxas makes the first use of the
 //    CURRENT word wait on the scoreboard of the load just issued for the NEXT one (27 % of all warp
-//    stall samples on that instruction, profiles/r01g);
+//    stall samples on that instruction, profiles/r01g_pa4_fused_stalls.txt);
 //  * cp.async (LDGSTS) works but shares its completion scoreboard with the bulk stores
 //    (cp.async.wait_group and cp.async.bulk.wait_group.read are the same DEPBAR.LE SB0), so a
 //    wait for the rows is also a wait for the warp's output tiles - which rules out keeping one
