@@ -11,6 +11,8 @@ Checkers).  Here the same data flow runs for B envs at once and never leaves HBM
   one launch per step with `policy(obs) -> actions`), with in-kernel episode reset, and returns
   the transitions as `[T, B, ...]` device tensors under the reference's variable names.  "next"
   fields are views of the same rollout buffer shifted by one step: nothing is copied.
+* `evaluate_episodes(env, policy)` is the reference's evaluation loop (alg/evaluate.py) over the
+  batch: one episode per env, reward sums masked at each env's own first `done`.
 * `process_batch(...)` re-expresses the reference's batch formatting on the device: one row per
   (time step, env, agent), global quantities repeated per agent, one-hot actions and the
   other-agents' action blocks, in the reference's return order.
@@ -146,6 +148,46 @@ class TransitionCollector(object):
         return (S, tr["global_state"].reshape(S, N, 4), flat(tr["obs_others"]), flat(tr["obs_self"]), a1, ao,
                 rep(tr["reward"]), flat(tr["reward_n"]), tr["global_state_next"].reshape(S, N, 4),
                 flat(tr["obs_others_next"]), flat(tr["obs_self_next"]), done, goals)
+
+
+def evaluate_episodes(env, policy, l_action=5, reset_kwargs=None):
+    """Vectorised statement of the reference's evaluation loops (alg/evaluate.py:87-123 test_particle,
+    :159-203 test_checkers): every one of the B envs plays ONE episode from a fresh reset under
+    `policy(obs) -> actions [B, N]` (the caller's greedy actor; `obs` holds the observation fields plus
+    `actions_prev` and `goals`), rewards are summed until the env's own first `done`, and the sums are
+    averaged over the envs - B takes the place of n_eval.
+
+    Returns (reward_local_mean [N], reward_global_mean, info) as device tensors; info has
+    `episode_len` [B] and, like test_checkers' printout, `action_distribution` [N, l_action].
+    No host synchronisation inside the loop: all envs are stepped max_steps times (an env that is
+    done earlier keeps stepping, as the reference's env would, but is masked out of the sums)."""
+    col = TransitionCollector(env, l_action=l_action)
+    obs = dict(col.reset(**(reset_kwargs or {})))
+    B, N, dev = env.B, env.N, env.device
+    goals = col.goals()
+    local_key = "local_rewards" if col.is_checkers else "reward_n"
+    acc = torch.float64
+    reward_local = torch.zeros(B, N, dtype=acc, device=dev)
+    reward_global = torch.zeros(B, dtype=acc, device=dev)
+    dist_action = torch.zeros(N, l_action, dtype=acc, device=dev)
+    episode_len = torch.zeros(B, dtype=torch.int32, device=dev)
+    alive = torch.ones(B, dtype=torch.bool, device=dev)
+    prev = torch.zeros(B, N, dtype=torch.int8, device=dev)   # evaluate.py:181: actions_prev starts at zero
+    for _ in range(int(env.max_steps)):
+        obs["actions_prev"], obs["goals"] = prev, goals
+        a = policy(obs).to(torch.int8).reshape(B, N)
+        out = env.step(a)
+        w = alive.to(acc)
+        reward_local += out[local_key].to(acc) * w.unsqueeze(-1)
+        reward_global += out["reward"].to(acc) * w
+        onehot = torch.nn.functional.one_hot(a.to(torch.int64).clamp(0, l_action - 1), l_action).to(acc)
+        dist_action += (onehot * w.view(B, 1, 1)).sum(dim=0)
+        episode_len += alive.to(torch.int32)
+        alive = alive & (out["done"] == 0)
+        prev = a
+        obs = {k: out[k] for k in col.obs_fields}
+    info = {"episode_len": episode_len, "action_distribution": dist_action / dist_action.sum().clamp(min=1)}
+    return reward_local.mean(dim=0), reward_global.mean(), info
 
 
 def split_good_bad(tr, collisions_before, collisions_after):

@@ -8,7 +8,7 @@ import torch
 
 import oracle
 from cm3_b200 import VecCheckers, VecParticle, presets
-from cm3_b200.rollout import TransitionCollector, numpy_process_actions
+from cm3_b200.rollout import TransitionCollector, evaluate_episodes, numpy_process_actions
 
 pytestmark = pytest.mark.gpu
 
@@ -126,3 +126,73 @@ def test_particle_random_goals_are_tracked_per_step():
         for t in range(T - 1):
             changed = not np.array_equal(goals[t + 1, b], goals[t, b])
             assert changed == done[t, b], (b, t)
+
+
+def test_evaluate_episodes_matches_the_reference_evaluation_loop():
+    """evaluate.py:159-203 (test_checkers) and :87-123 (test_particle) replayed per env on the oracle
+    with the same deterministic policy: per-agent and global reward sums up to each env's own first
+    done, averaged over the envs; episode lengths; action distribution."""
+    B = 96
+    ctor = dict(presets.CHECKERS["stage2"], max_steps=presets.MAX_STEPS)
+    env = VecCheckers(B, **ctor)
+    step_no = {"t": 0}
+
+    def policy(obs):  # depends on what the reference's actor sees: own vector, previous actions
+        step_no["t"] += 1
+        r = obs["vec"][:, :, 0].long() + obs["vec"][:, :, 1].long() + obs["actions_prev"].long() + step_no["t"]
+        return r % 5
+
+    rl, rg, info = evaluate_episodes(env, policy, reset_kwargs=dict(goals=np.eye(2)))
+    orc = oracle.OracleCheckers(B, **ctor)
+    out = orc.reset(np.array([[0, 1]]))
+    prev = np.zeros((B, 2), dtype=np.int64)
+    alive = np.ones(B, dtype=bool)
+    loc, glob, length = np.zeros((B, 2)), np.zeros(B), np.zeros(B, dtype=np.int64)
+    dist = np.zeros((2, 5))
+    for t in range(1, presets.MAX_STEPS + 1):
+        a = (out["vec"][:, :, 0].astype(np.int64) + out["vec"][:, :, 1].astype(np.int64) + prev + t) % 5
+        out = orc.step(a.astype(np.int8))
+        loc += out["local_rewards"] * alive[:, None]
+        glob += out["reward"] * alive
+        length += alive
+        for n in range(2):
+            dist[n] += np.bincount(a[alive, n], minlength=5)
+        alive &= ~out["done"].astype(bool)
+        prev = a
+    assert not alive.any()  # every episode ends by max_steps (checkers.py:246)
+    np.testing.assert_allclose(rl.cpu().numpy(), loc.mean(axis=0), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(float(rg), glob.mean(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(info["episode_len"].cpu().numpy(), length)
+    np.testing.assert_allclose(info["action_distribution"].cpu().numpy(), dist / dist.sum(), rtol=1e-12)
+
+    # particle: goals are the landmark positions (evaluate.py:96-98); policy walks towards them
+    N, cfg = 4, presets.PARTICLE["cross"]   # episodes end between step 22 and max_steps, some contacts
+    pe = VecParticle(B, N, cfg, max_steps=50, dtype=torch.float64)
+
+    def seek(obs):
+        d = obs["goals"] - obs["obs_self"][:, :, 2:4]
+        horiz = d[:, :, 0].abs() >= d[:, :, 1].abs()
+        return torch.where(horiz, torch.where(d[:, :, 0] > 0, 2, 1), torch.where(d[:, :, 1] > 0, 4, 3))
+
+    pos = np.tile(np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1), (B, 1, 1)).astype(np.float64)
+    pos += np.random.default_rng(11).normal(0, 0.03, pos.shape)  # no exactly head-on (coincident) meetings
+    lm = np.tile(np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1), (B, 1, 1)).astype(np.float64)
+    rl, rg, info = evaluate_episodes(pe, seek, reset_kwargs=dict(init_pos=pos, init_landmarks=lm))
+    po = oracle.OracleParticle(B, N, max_steps=50)
+    out = po.reset_to(pos, lm)
+    alive = np.ones(B, dtype=bool)
+    loc, glob, length = np.zeros((B, N)), np.zeros(B), np.zeros(B, dtype=np.int64)
+    for t in range(50):
+        d = lm - out["obs_self"][:, :, 2:4]
+        horiz = np.abs(d[:, :, 0]) >= np.abs(d[:, :, 1])
+        a = np.where(horiz, np.where(d[:, :, 0] > 0, 2, 1), np.where(d[:, :, 1] > 0, 4, 3)).astype(np.int8)
+        out = po.step(a)
+        loc += out["reward_n"] * alive[:, None]
+        glob += out["reward"] * alive
+        length += alive
+        alive &= ~out["done"].astype(bool)
+    assert np.isfinite(loc).all()
+    np.testing.assert_array_equal(info["episode_len"].cpu().numpy(), length)
+    np.testing.assert_allclose(rl.cpu().numpy(), loc.mean(axis=0), rtol=1e-7)
+    np.testing.assert_allclose(float(rg), glob.mean(), rtol=1e-7)
+    assert length.min() < 50 < length.max() + 1  # early all-reached endings and max_steps endings
