@@ -45,6 +45,43 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.ParticleOutputs) == 48
 
 
+def test_header_is_plain_c_and_layouts_match_the_ctypes_binding(tmp_path):
+    """include/cm3env.h compiles as C11 (no C++ leaking through the boundary) and every field of
+    every struct sits at the offset the ctypes binding assumes."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"cm3_checkers_config": L.CheckersConfig, "cm3_checkers_state": L.CheckersState,
+               "cm3_checkers_outputs": L.CheckersOutputs, "cm3_particle_config": L.ParticleConfig,
+               "cm3_particle_state": L.ParticleState, "cm3_particle_outputs": L.ParticleOutputs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cm3env.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append('printf("abi %d max_agents %d max_dst %d\\n", CM3_ABI_VERSION, CM3_MAX_AGENTS, CM3_MAX_DST);')
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    seen = 0
+    for line in out:
+        parts = line.split()
+        if len(parts) == 3 and parts[0] in structs:
+            ct = structs[parts[0]]
+            want = C.sizeof(ct) if parts[1] == "sizeof" else getattr(ct, parts[1]).offset
+            assert int(parts[2]) == want, line
+            seen += 1
+        elif parts and parts[0] == "abi":
+            assert (int(parts[1]), int(parts[3]), int(parts[5])) == (L.load_library().cm3_abi_version(), L.MAX_AGENTS, L.MAX_DST)
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
+
+
 def test_bad_geometry_is_rejected_like_the_reference():
     lib = L.load_library()
     cfg = L.CheckersConfig(n_rows=4, n_columns=8, n_obs=2, n_agents=2, max_steps=33, num_envs=4)
