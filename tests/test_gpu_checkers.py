@@ -106,6 +106,29 @@ def test_rollout_equals_stepping_and_is_bit_exact():
     np.testing.assert_array_equal(st["steps"], orc.steps())
 
 
+@pytest.mark.parametrize("N,B", [(1, 1024), (3, 264), (4, 512), (1, 1001), (3, 250)])
+def test_rollout_equals_stepping_for_every_agent_count(N, B):
+    """The multi-step launch (action rows streamed through shared memory) against single-step
+    launches for the agent counts the CK2 test above does not cover.  B = 1001 / 250: ragged last
+    tile, and for N = 3 rows that are not 4-byte aligned (direct action loads)."""
+    ctor = dict(n_rows=3, n_columns=8, n_obs=2, agents_r=[0, 2, 1, 1][:N], agents_c=[8, 8, 8, 7][:N],
+                n_agents=N, max_steps=40)
+    T = 47  # runs past max_steps: without auto_reset both paths keep stepping the finished episode
+    rng = np.random.default_rng(10 * N + B)
+    actions = rng.integers(0, 5, size=(T, B, N)).astype(np.int8)
+    goals = np.eye(2)[rng.integers(0, 2, size=N)]
+    e1, e2 = VecCheckers(B, **ctor), VecCheckers(B, **ctor)
+    e1.reset(goals=goals); e2.reset(goals=goals)
+    ro = e1.rollout(T, actions=actions)
+    for t in range(T):
+        out = e2.step(actions[t])
+        for f in gu.CHECKERS_FIELDS:
+            assert torch.equal(out[f], ro[f][t]), (t, f)
+    assert bool(ro["done"][39].all())
+    for k in e1.state:
+        assert torch.equal(e1.state[k], e2.state[k]), k
+
+
 def test_philox_actions_match_cpu_twin_and_shard_invariance():
     B, T = 1024, 12
     env = VecCheckers(B, **CK2)
