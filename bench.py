@@ -45,6 +45,7 @@ SEED = 12341        # alg/config.json:6
 MAX_STEPS = 33      # alg/config.json:61
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 NVLINK_PEER_GBS = 770.0    # B200_PROFILING.md: measured peer copy, per direction per GPU (900 nominal)
+SPIN_CYCLES = 4_000_000    # ~2 ms of device spin queued ahead of a timed region (see timed_steps)
 
 
 def workload_spec(name):
@@ -185,23 +186,40 @@ def ncu_traffic(kernel_key):
     return None
 
 
-class StepRunner(object):
-    """K single-step launches into a rollout ring, replayed from a CUDA graph."""
+REF_FIELDS = None  # env facades' REF_FIELDS: the reference's return tuple, nothing else, is written and counted
 
-    def __init__(self, env, spec, ring, seed):
+
+def ref_fields(env):
+    from cm3_b200 import vec_checkers, vec_particle
+    return vec_checkers.REF_FIELDS if hasattr(env, "n_rows") else vec_particle.REF_FIELDS
+
+
+class StepRunner(object):
+    """K single-step launches into a rollout ring > L2, replayed from a CUDA graph of `ring` steps.
+    chained=True: cm3_*_step_chained (tile i of step k+1 waits for tile i of step k only);
+    chained=False: plain stream order + programmatic dependent launch (round 1's per-step mode)."""
+
+    def __init__(self, env, spec, ring, seed, chained=True):
         import torch
-        self.torch, self.env, self.ring = torch, env, ring
-        self.ring_out = env.alloc_outputs(ring)
+        self.torch, self.env, self.ring, self.chained = torch, env, ring, chained
+        self.ring_out = env.alloc_outputs(ring, fields=ref_fields(env))
         g = torch.Generator(device="cpu").manual_seed(seed)
         acts = torch.randint(0, 5, (ring, env.B, env.N), generator=g, dtype=torch.int8)
         self.actions = acts.to(env.device)
-        self.slots = [{k: v[t] for k, v in self.ring_out.items()} for t in range(ring)]
+        # everything a launch needs is built here, once: per-slot output structs and action slices
+        self.slots = [env._outputs_struct({k: v[t] for k, v in self.ring_out.items()}) for t in range(ring)]
+        self.acts = [self.actions[t] for t in range(ring)]
         self.graph = None
+        self.launches = 0
 
     def launch(self, t):
-        # one kernel launch: T=1 rollout with in-kernel episode reset, outputs -> ring slot
-        self.env.rollout(1, actions=self.actions[t % self.ring:t % self.ring + 1], auto_reset=True,
-                         out={k: v.unsqueeze(0) for k, v in self.slots[t % self.ring].items()})
+        # one kernel launch: one step with in-kernel episode reset, outputs -> ring slot
+        i = t % self.ring
+        if self.chained:
+            self.env.step_chained(self.acts[i], self.slots[i], seed=SEED, t0=t, auto_reset=True)
+        else:
+            self.env.rollout(1, actions=self.actions[i:i + 1], auto_reset=True, t0=t,
+                             out={k: v[i:i + 1] for k, v in self.ring_out.items()})
 
     def capture(self):
         torch = self.torch
@@ -222,29 +240,46 @@ class StepRunner(object):
             self.graph.replay()
         for t in range(rem):
             self.launch(t)
+        self.launches += k
 
 
 class FusedRunner(object):
-    """K steps as K/T launches of the T-step kernel reading the pre-generated action stream."""
+    """K steps as K/T launches of the T-step kernel reading the pre-generated action stream.  The
+    launches are planned (ctypes arguments built once, VecCheckers.plan_rollout), so the host path of
+    the timed region is the foreign call alone."""
 
     def __init__(self, env, T, seed):
         import torch
         self.env, self.T = env, T
         g = torch.Generator(device="cpu").manual_seed(seed)
         self.actions = torch.randint(0, 5, (T, env.B, env.N), generator=g, dtype=torch.int8).to(env.device)
-        self.out = env.alloc_outputs(T)
+        self.out = env.alloc_outputs(T, fields=ref_fields(env))
+        self.plans = {T: env.plan_rollout(T, actions=self.actions, out=self.out, auto_reset=True, seed=SEED)}
         self.launches = 0
+        self.t = 0
+
+    def plan_for(self, n):
+        if n not in self.plans:
+            self.plans[n] = self.env.plan_rollout(n, actions=self.actions[:n].contiguous(), auto_reset=True, seed=SEED,
+                                                  out={f: v[:n] for f, v in self.out.items()})
+        return self.plans[n]
 
     def capture(self):
         pass
 
+    def prepare(self, k):
+        if k % self.T:
+            self.plan_for(k % self.T)
+
     def run(self, k):
         n_full, rem = divmod(k, self.T)
+        full = self.plans[self.T]
         for _ in range(n_full):
-            self.env.rollout(self.T, actions=self.actions, auto_reset=True, out=self.out)
+            full(self.t)
+            self.t += self.T
         if rem:
-            self.env.rollout(rem, actions=self.actions[:rem], auto_reset=True,
-                             out={f: v[:rem] for f, v in self.out.items()})
+            self.plan_for(rem)(self.t)
+            self.t += rem
         self.launches += n_full + (1 if rem else 0)
 
 
@@ -253,7 +288,13 @@ def bytes_per_env_step(env):
 
 
 def timed_steps(runner, K, W, world, device, local_rank, sample_clocks=True):
-    """W warm-up steps, then exactly K timed steps; returns (ms max over ranks, clocks)."""
+    """W warm-up steps, then exactly K timed steps.  Returns (ms max over ranks, clocks, per-rank ms).
+
+    The event pair brackets device time only: a spin kernel (torch.cuda._sleep) is queued ahead
+    of the first event, so that every launch of the K steps is already enqueued when the GPU
+    reaches it - host enqueue latency and Python overhead are outside the pair.  (Round 1 recorded
+    the first event on an idle stream: with the driver's K = 20 the single 190 us launch was timed
+    together with the host's call path and read 0.59 of the roofline where ncu showed 0.98.)"""
     import torch
     import torch.distributed as dist
 
@@ -263,12 +304,16 @@ def timed_steps(runner, K, W, world, device, local_rank, sample_clocks=True):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if hasattr(runner, "prepare"):
+        runner.prepare(W)
+        runner.prepare(K)
     runner.run(W)
     sampler = ClockSampler(local_rank) if sample_clocks else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if sampler:
         sampler.start()
+    torch.cuda._sleep(SPIN_CYCLES)
     e0.record()
     runner.run(K)
     e1.record()
@@ -277,11 +322,14 @@ def timed_steps(runner, K, W, world, device, local_rank, sample_clocks=True):
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
+    per_rank = [ms]
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return ms, clocks
+        allt = torch.zeros(world, device=device, dtype=torch.float64)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank = [float(x) for x in allt.tolist()]
+        ms = max(per_rank)
+    return ms, clocks, per_rank
 
 
 class GatherRunner(object):
@@ -290,10 +338,10 @@ class GatherRunner(object):
     [T, total_envs, ...] - by ncclAllGather ("nccl") or by the kernel's own peer stores over
     NVLink ("peer", cm3_*_rollout_gather).  One "step" is still one env step of the whole batch."""
 
-    def __init__(self, env, shard, T, mode):
+    def __init__(self, env, shard, T, mode, overlap=True):
         from cm3_b200.sharding import RolloutAllGather
         self.env, self.T = env, T
-        self.g = RolloutAllGather(env, T, shard=shard, mode=mode)
+        self.g = RolloutAllGather(env, T, shard=shard, mode=mode, fields=ref_fields(env), double_buffer=overlap)
         self.mode = self.g.mode
         self.launches = 0
 
@@ -306,7 +354,11 @@ class GatherRunner(object):
             self.launches += 1
 
 
-def run_gpu(args):
+KERNEL_NAMES = {"ck2": "checkers_kernel<StaticGeo<3,8,2>,2,float,float>", "ck1": "checkers_kernel<StaticGeo<3,8,2>,1,float,float>",
+                "pa4": "particle_kernel<4,float,0,1>", "pa3": "particle_kernel<3,float,0,1>", "pm2": "particle_kernel<2,float,0,1>"}
+
+
+def setup_dist():
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -329,7 +381,58 @@ def run_gpu(args):
             os.dup2(saved, 1)
             os.close(saved)
     torch.cuda.set_device(local_rank)
-    device = "cuda:%d" % local_rank
+    return rank, world, local_rank, "cuda:%d" % local_rank
+
+
+def fused_bytes(env, spec, T, with_actions=True):
+    """Algorithmic bytes per env-step of a T-step launch: outputs (+ the action stream) + state / T."""
+    out_b = env.out_bytes_per_env_step()
+    state_b = env.bytes_per_env_step() - out_b - spec["n"]
+    return out_b + (spec["n"] if with_actions else 0) + state_b / T
+
+
+def measure_workload(spec, wl, B, K, W, rank, world, device, local_rank, peak, modes=("fused", "step"), sample_clocks=True):
+    """One workload on this rank's GPU (all ranks call it together): fused 33-step launches with the
+    action stream from HBM, then one chained launch per step from a CUDA graph.  Returns a dict of
+    whole-job numbers (max over ranks)."""
+    import torch
+    T = MAX_STEPS
+    env = make_env(spec, B, device, env_id_offset=rank * B)
+    bpe = bytes_per_env_step(env)
+    res = {"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"], "n_gpus": world,
+           "kernel": KERNEL_NAMES.get(wl)}
+    if "fused" in modes:
+        runner = FusedRunner(env, T, SEED + rank)
+        Kf = max(T, K // T * T)
+        ms, clocks, per_rank = timed_steps(runner, Kf, max(W, T), world, device, local_rank, sample_clocks)
+        fb = fused_bytes(env, spec, T)
+        ach = fb * B * Kf / (ms * 1e-3) / 1e9
+        res["fused"] = {"value": world * B * spec["n"] * Kf / (ms * 1e-3), "unit": UNIT, "steps": Kf, "launches": Kf // T,
+                        "us_per_step": ms * 1e3 / Kf, "achieved_gbs": ach, "frac": ach / peak,
+                        "algorithmic_bytes_per_env_step": fb, "per_rank_ms": per_rank, "clocks": clocks}
+        del runner
+    ring = min(4096, max(T, int(np.ceil(512e6 / (bpe * B)))))
+    for name, chained in (("per_step_chained", True), ("per_step_stream_ordered", False)):
+        if name in modes or "step" in modes:
+            runner = StepRunner(env, spec, ring, SEED + rank, chained=chained)
+            runner.capture()
+            Ks = max(ring, K // ring * ring)
+            ms, clocks, per_rank = timed_steps(runner, Ks, ring, world, device, local_rank, sample_clocks)
+            ach = bpe * B * Ks / (ms * 1e-3) / 1e9
+            res[name] = {"value": world * B * spec["n"] * Ks / (ms * 1e-3), "unit": UNIT, "steps": Ks, "launches": Ks,
+                         "us_per_step": ms * 1e3 / Ks, "achieved_gbs": ach, "frac": ach / peak,
+                         "algorithmic_bytes_per_env_step": bpe, "rollout_ring_slots": ring, "per_rank_ms": per_rank,
+                         "clocks": clocks}
+            del runner
+    del env
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local_rank, device = setup_dist()
     spec = workload_spec(args.workload)
     B, K, W = args.envs, args.steps, args.warmup
     env = make_env(spec, B, device, env_id_offset=rank * B)
@@ -341,87 +444,85 @@ def run_gpu(args):
     W = max(W, 3)
     out_b = env.out_bytes_per_env_step()
     state_b = bpe - out_b - spec["n"]
-    fused_bpe = out_b + spec["n"] + state_b / T
+    fused_bpe = fused_bytes(env, spec, T)
     launch_cfg = None
     if args.gather != "none":
         from cm3_b200.sharding import EnvShard
         K = max(T, K // T * T)
         W = (W + T - 1) // T * T
-        runner = GatherRunner(env, EnvShard(world * B, rank=rank, world=world, local_rank=local_rank), T, args.gather)
+        runner = GatherRunner(env, EnvShard(world * B, rank=rank, world=world, local_rank=local_rank), T, args.gather,
+                              overlap=not args.no_overlap)
         gather_mode = runner.mode
         mode = "gather"
     elif args.mode == "fused":
         runner = FusedRunner(env, T, SEED + rank)
         mode = "fused"
     else:
-        runner = StepRunner(env, spec, ring, SEED + rank)
-        mode = "step"
+        runner = StepRunner(env, spec, ring, SEED + rank, chained=args.mode == "step")
+        mode = args.mode
     runner.capture()
-    ms, clocks = timed_steps(runner, K, W, world, device, local_rank)
+    l0 = runner.launches
+    ms, clocks, per_rank = timed_steps(runner, K, W, world, device, local_rank)
+    # launches inside the timed region: everything the runner issued minus the warm-up's share
+    timed_launches = {"fused": (K + T - 1) // T, "gather": K // T}.get(mode, K)
     value = world * B * spec["n"] * K / (ms * 1e-3)
     peak, peak_src = hbm_peak()
     step_us = ms * 1e3 / K
-    if mode == "step":
+    if mode in ("step", "step_ordered"):
         eff_bpe, launches, launch_us = bpe, K, step_us
-        launch_cfg = {"launch": "1 kernel launch per step, replayed from a CUDA graph of %d steps" % ring,
+        launch_cfg = {"launch": "1 kernel launch per step (%s), replayed from a CUDA graph of %d steps" % (
+                          "cm3_*_step_chained: per-tile ticket chaining" if mode == "step" else "stream order + programmatic dependent launch", ring),
                       "rollout_ring_slots": ring,
                       "l2": "outputs go to a %d-slot rollout ring of %.0f MB (> 126 MB L2); no explicit flush" % (ring, ring * bpe * B / 1e6)}
     else:
-        eff_bpe, launches = fused_bpe, (K + T - 1) // T
+        # the bytes of the launches actually issued: whole 33-step launches + one shorter remainder
+        n_full, rem = divmod(K, T)
+        launches = timed_launches
+        eff_bpe = (out_b + spec["n"]) + state_b * launches / K
         launch_us = ms * 1e3 / launches
-        launch_cfg = {"launch": "1 kernel launch per %d steps (one episode): state stays in registers between the steps of a launch" % T,
+        launch_cfg = {"launch": "1 kernel launch per %d steps (one episode): state stays in registers between the steps of a launch; K = %d steps = %d launch(es) of %d%s" % (
+                          T, K, n_full, T, (" + 1 of %d" % rem) if rem else ""),
                       "l2": "every step writes all its outputs to a [%d][B] rollout buffer of %.0f MB (> 126 MB L2), overwritten by the next launch; no explicit flush" % (T, out_b * B * T / 1e6)}
     achieved = eff_bpe * B / (step_us * 1e-6) / 1e9
-    kernel_key = "%s_%s" % (args.workload, "step" if mode == "step" else "rollout")
-    kname = {"ck2": "checkers_kernel<3,8,2,2,float,float>", "ck1": "checkers_kernel<3,8,2,1,float,float>",
-             "pa4": "particle_kernel<4,float>", "pa3": "particle_kernel<3,float>", "pm2": "particle_kernel<2,float>"}[args.workload]
+    kernel_key = "%s_%s" % (args.workload, "step" if mode.startswith("step") else "rollout")
+    kname = KERNEL_NAMES[args.workload]
 
+    config = dict({"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"], "mode": mode,
+                   "actions": "uniform int8 in 0..4, a [33][B][N] stream pre-generated in HBM and read by every step",
+                   "auto_reset": True,
+                   "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world,
+                   "timing": "CUDA events on the launching stream behind a %d-cycle device spin (all launches enqueued before the first event fires); barrier + synchronize both sides; max over ranks" % SPIN_CYCLES},
+                  **launch_cfg)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 bitboard state, f32 outputs" if spec["kind"] == "checkers" else "f32",
         "data": "synthetic",
-        "config": dict({"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"], "mode": mode,
-                        "actions": "uniform int8 in 0..4, a [33][B][N] stream pre-generated in HBM and read by every step",
-                        "auto_reset": True,
-                        "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world}, **launch_cfg),
+        "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(kernel_key),
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": eff_bpe,
                      "bytes_per_launch": eff_bpe * B * (K / launches), "launch_us": launch_us, "kernel": kname},
         "gpu_launches": launches,
+        "per_rank_ms": per_rank,
         "clocks": clocks,
     }
     if gather_mode is not None:
         sent = out_b * B * (world - 1)  # bytes this GPU delivers to its peers per env step
-        launch_us = step_us
         out["gpu_launches"] = K // T
         out["config"].update({"launch": "1 launch per %d fused env steps, device Philox actions" % T,
                               "actions": "Philox4x32-10 on the device, keyed by (seed, global env id, step)",
-                              "rollout_all_gather": gather_mode,
+                              "rollout_all_gather": gather_mode, "overlap": "two symmetric buffers: rollout k+1 runs while the stores of rollout k drain" if not args.no_overlap else "none",
                               "l2": "gathered rollout buffer [%d][%d envs] = %.0f MB per GPU (> 126 MB L2 when >= 2 GPUs at the default size)" % (T, world * B, out_b * world * B * T / 1e6)})
-        hbm_written = (out_b + state_b / T) * world * B / (step_us * 1e-6) / 1e9  # the whole gathered batch lands in this GPU's HBM
-        nv = sent / (step_us * 1e-6) / 1e9 if world > 1 else 0.0
-        out["roofline"] = {"bound": "nvlink" if world > 1 else "hbm", "achieved": nv if world > 1 else hbm_written,
-                           "peak": NVLINK_PEER_GBS if world > 1 else peak, "unit": "GB/s",
-                           "frac": (nv / NVLINK_PEER_GBS) if world > 1 else hbm_written / peak, "traffic": None,
-                           "peak_source": "measured peer-copy reference, B200_PROFILING.md (770 GB/s per direction per GPU; 900 nominal)" if world > 1 else peak_src,
-                           "kernel": "%s rollout_gather (%s)" % (kname, gather_mode),
-                           "nvlink_bytes_sent_per_gpu_per_step": sent, "nvlink_gbs_per_gpu": nv,
-                           "hbm_gbs_written_per_gpu": hbm_written, "hbm_frac": hbm_written / peak,
-                           "algorithmic_bytes_per_env_step": out_b + state_b / T,
-                           "bytes_per_launch": (out_b + state_b / T) * world * B * T, "launch_us": step_us * T,
-                           "note": "every output byte of a shard is delivered to each of the other %d GPU(s): the exchange, not the stepper, bounds this configuration" % (world - 1)}
-    if args.gather != "none":
-        pass  # the collective run reports the kernel-side number only
+        out["roofline"] = gather_roofline(out_b, state_b, T, B, world, step_us, peak, peak_src, kname, gather_mode)
     else:
-        out["e2e"] = measure_e2e(env, spec, args, world)   # all ranks take part
-        if rank == 0 and not args.no_extras:
-            out["extra"] = measure_extras(env, spec, args, peak, mode, world, device, local_rank, ring)
-            if spec["kind"] == "checkers":
-                out["extra"]["e2e_int8_tiles"] = measure_e2e_int8(spec, args, device)
-            if world == 1:
-                out["cpu_baseline"] = cpu_baseline(spec, args)
+        out["e2e"] = measure_e2e(spec, args, world, rank, device)   # all ranks take part
+        if not args.no_extras:
+            extra = measure_extras(env, spec, args, peak, mode, world, rank, device, local_rank, ring)
+            if rank == 0:
+                out["extra"] = extra
+                if world == 1:
+                    out["cpu_baseline"] = cpu_baseline(spec, args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,90 +530,249 @@ def run_gpu(args):
         print(json.dumps(out))
 
 
-def measure_e2e(env, spec, args, world=1):
-    """The same metric through the host-buffer entry point (cm3_*_step_host): each step copies the
-    step's actions from pinned host memory to the device, launches the kernel and copies EVERY
-    output field back into pinned host memory, then waits.  With world > 1 every rank drives its
-    own GPU (own PCIe link) at the same time; the value is the whole job's, from the slowest rank."""
+def gather_roofline(out_b, state_b, T, B, world, step_us, peak, peak_src, kname, gather_mode):
+    sent = out_b * B * (world - 1)
+    hbm_written = (out_b + state_b / T) * world * B / (step_us * 1e-6) / 1e9  # the whole gathered batch lands in this GPU's HBM
+    nv = sent / (step_us * 1e-6) / 1e9 if world > 1 else 0.0
+    return {"bound": "nvlink" if world > 1 else "hbm", "achieved": nv if world > 1 else hbm_written,
+            "peak": NVLINK_PEER_GBS if world > 1 else peak, "unit": "GB/s",
+            "frac": (nv / NVLINK_PEER_GBS) if world > 1 else hbm_written / peak, "traffic": None,
+            "peak_source": "measured peer-copy reference, B200_PROFILING.md (770 GB/s per direction per GPU; 900 nominal)" if world > 1 else peak_src,
+            "kernel": "%s rollout_gather (%s)" % (kname, gather_mode),
+            "nvlink_bytes_sent_per_gpu_per_step": sent, "nvlink_gbs_per_gpu": nv,
+            "hbm_gbs_written_per_gpu": hbm_written, "hbm_frac": hbm_written / peak,
+            "algorithmic_bytes_per_env_step": out_b + state_b / T,
+            "bytes_per_launch": (out_b + state_b / T) * world * B * T, "launch_us": step_us * T,
+            "note": "every output byte of a shard is delivered to each of the other %d GPU(s): the exchange, not the stepper, bounds this configuration" % (world - 1)}
+
+
+def _max_over_ranks(x, world, device):
     import torch
     import torch.distributed as dist
-    B, N = env.B, env.N
-    rng = np.random.default_rng(SEED)
-    acts = rng.integers(0, 5, size=(8, B, N)).astype(np.int8)
-    steps = max(3, min(args.e2e_steps, args.steps))
-    for t in range(3):
-        env.step_host(acts[t % 8])
-    torch.cuda.synchronize()
     if world > 1:
-        dist.barrier()
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return x
+
+
+def measure_e2e(spec, args, world=1, rank=0, device="cuda:0"):
+    """The same metric end to end through the host-buffer API: every step copies that step's
+    actions from pinned host memory to the device, runs the step kernel and copies EVERY output
+    field of the step back into pinned host memory.
+
+    Headline `value`: VecCheckers/VecParticle.rollout_host -> cm3_*_rollout_host, which double
+    buffers the device side (the D2H copy of step t overlaps the kernel of step t + 1), with the
+    lossless compact encoding for Checkers (grid / obs_self_t as int8: their values are always in
+    {-1, 0, +1}).  `unpipelined_fp32` is round 1's call, step_host with fp32 tiles: copy, kernel,
+    copy in series.  With world > 1 every rank drives its own GPU (own PCIe link) at the same
+    time; values are the whole job's, from the slowest rank."""
+    import torch
+    import torch.distributed as dist
+    from cm3_b200 import VecCheckers
+    B, N = args.envs, spec["n"]
+    T = MAX_STEPS
+    rng = np.random.default_rng(SEED)
+    acts = rng.integers(0, 5, size=(T, B, N)).astype(np.int8)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    res = {}
+    # (a) pipelined, compact
+    if spec["kind"] == "checkers":
+        env = VecCheckers(B, device=device, tile_dtype=torch.int8, env_id_offset=rank * B, **spec["ctor"])
+        env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
+        enc = "grid / obs_self_t int8 (lossless: values in {-1,0,+1}), vectors and rewards fp32"
+    else:
+        env = make_env(spec, B, device, env_id_offset=rank * B)
+        enc = "fp32"
+    env.rollout_host(acts)  # warm-up (allocates the pinned areas)
+    reps = max(1, min(3, args.e2e_steps // T)) if args.e2e_steps >= T else 1
+    Th = T if args.e2e_steps >= T else max(3, args.e2e_steps)
+    a = acts[:Th]
+    env.rollout_host(a)
+    sync_all()
+    t0 = time.perf_counter()
+    for r in range(reps):
+        out = env.rollout_host(a, t0=r * Th)
+    float(out["reward"][-1, 0])
+    el = _max_over_ranks(time.perf_counter() - t0, world, device)
+    bo = sum(v[0].nbytes for v in out.values())
+    steps = reps * Th
+    res.update({"value": world * B * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": world * B * N,
+                "d2h_bytes_per_step": world * int(bo), "n_gpus": world, "steps": steps, "ms_per_step": el * 1e3 / steps,
+                "api": "Vec*.rollout_host -> cm3_*_rollout_host: per step H2D of the step's actions (pinned), kernel, D2H of every output field (pinned); the D2H of step t overlaps the kernel of step t+1",
+                "encoding": enc, "d2h_gbs_per_gpu": bo * steps / el / 1e9,
+                "note": "in-kernel episode reset on; PCIe-bound: %.1f MB D2H per step per GPU" % (bo / 1e6)})
+    del env
+    # (b) round 1's path: step_host, fp32 tiles, copy / kernel / copy in series
+    env = make_env(spec, B, device, env_id_offset=rank * B)
+    steps = max(3, min(args.e2e_steps, 30))
+    for t in range(3):
+        env.step_host(acts[t % T])
+    sync_all()
     t0 = time.perf_counter()
     for t in range(steps):
-        out = env.step_host(acts[t % 8])
+        out = env.step_host(acts[t % T])
     float(out["reward"][0])
-    el = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([el], device=env.device, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        el = float(tt.item())
+    el = _max_over_ranks(time.perf_counter() - t0, world, device)
     bo = sum(v.nbytes for v in out.values())
-    return {"value": world * B * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": world * B * N,
-            "d2h_bytes_per_step": world * int(bo), "n_gpus": world,
-            "steps": steps, "ms_per_step": el * 1e3 / steps,
-            "api": "VecCheckers/VecParticle.step_host -> cm3_*_step_host (host actions in, all output fields out, pinned)",
-            "note": "no auto-reset on this path (reference semantics); PCIe-bound: %.1f MB D2H per step" % (bo / 1e6)}
-
-
-def measure_e2e_int8(spec, args, device):
-    """Checkers only: the same host-buffer call with grid / obs_self_t delivered as int8 (lossless:
-    their values are always in {-1, 0, +1}) - a quarter of the tile bytes over PCIe."""
-    import torch
-    from cm3_b200 import VecCheckers
-    env = VecCheckers(args.envs, device=device, tile_dtype=torch.int8, **spec["ctor"])
-    env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
-    res = measure_e2e(env, spec, args)
-    res["api"] = "VecCheckers(tile_dtype=int8).step_host -> cm3_checkers_step_host, cfg.tile = CM3_TILE_I8"
+    res["unpipelined_fp32"] = {"value": world * B * N * steps / el, "unit": UNIT, "d2h_bytes_per_step": world * int(bo),
+                               "steps": steps, "ms_per_step": el * 1e3 / steps,
+                               "api": "Vec*.step_host -> cm3_*_step_host_packed (fp32 tiles; no auto-reset: reference semantics)"}
+    del env
+    torch.cuda.empty_cache()
     return res
 
 
-def measure_extras(env, spec, args, peak, mode="fused", world=1, device="cuda:0", local_rank=0, ring=MAX_STEPS):
+def measure_dropin_latency(device):
+    """B = 1 drop-ins (the only form alg/train_onpolicy.py:302-350 can use unchanged): microseconds per
+    env.step through the reference's own API, beside the reference's Python step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "cm3_b200", "dropin"))
+    res = {}
+    try:
+        from cm3_b200 import presets
+        from env.checkers import Checkers   # the way a trainer imports it (train_offpolicy.py:24), dropin/ on sys.path
+        ck = presets.CHECKERS["stage2"]
+        env = Checkers(ck["n_rows"], ck["n_columns"], ck["n_obs"], ck["agents_r"], ck["agents_c"], ck["n_agents"], MAX_STEPS)
+        rng = np.random.default_rng(0)
+        env.reset(np.eye(2))
+        n = 600
+        acts = rng.integers(0, 5, size=(n, 2))
+        for t in range(50):
+            env.step(acts[t])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(n):
+            if t % MAX_STEPS == 0:
+                env.reset(np.eye(2))
+            env.step(acts[t])
+        res["checkers_stage2_us_per_step"] = (time.perf_counter() - t0) * 1e6 / n
+        res["checkers_reference_python_us_per_step"] = 94.0
+    except Exception as e:  # noqa: BLE001
+        res["checkers_error"] = repr(e)
+    try:
+        from multiagent.environment import MultiAgentEnv
+        import multiagent.scenarios as scenarios
+        from cm3_b200 import presets
+        scenario = scenarios.load("multi-goal_spread.py").Scenario()
+        world = scenario.make_world(4, presets.PARTICLE["antipodal"], 0.0)
+        env = MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation, None, scenario.done, max_steps=MAX_STEPS)
+        env.reset()
+        rng = np.random.default_rng(0)
+        n = 600
+        acts = rng.integers(0, 5, size=(n, 4))
+        for t in range(50):
+            env.step(acts[t])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(n):
+            if t % MAX_STEPS == 0:
+                env.reset()
+            env.step(acts[t])
+        res["particle_antipodal_us_per_step"] = (time.perf_counter() - t0) * 1e6 / n
+        res["particle_reference_python_us_per_step"] = 380.0
+    except Exception as e:  # noqa: BLE001
+        res["particle_error"] = repr(e)
+    res["note"] = "B = 1 drop-in facades stepping through the reference's API (resets included); reference figures: BASELINE.md section 2, probed in the build container"
+    return res
+
+
+def measure_gather(wl, B, mode, rank, world, device, local_rank, peak, peak_src, reps=6, overlap=True):
+    """BASELINE configs[3] as an `extra` line at world > 1 (all ranks call it)."""
+    from cm3_b200.sharding import EnvShard
+    spec = workload_spec(wl)
+    T = MAX_STEPS
+    env = make_env(spec, B, device, env_id_offset=rank * B)
+    try:
+        runner = GatherRunner(env, EnvShard(world * B, rank=rank, world=world, local_rank=local_rank), T, mode, overlap=overlap)
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+    ms, clocks, per_rank = timed_steps(runner, reps * T, 2 * T, world, device, local_rank, sample_clocks=False)
+    step_us = ms * 1e3 / (reps * T)
+    out_b = env.out_bytes_per_env_step()
+    state_b = env.bytes_per_env_step() - out_b - spec["n"]
+    r = gather_roofline(out_b, state_b, T, B, world, step_us, peak, peak_src, KERNEL_NAMES[wl], runner.mode)
+    return {"value": world * B * spec["n"] * reps * T / (ms * 1e-3), "unit": UNIT, "envs_per_gpu": B, "total_envs": world * B,
+            "mode": runner.mode, "overlap": overlap, "us_per_step": step_us, "launches": reps, "per_rank_ms": per_rank,
+            "nvlink_gbs_per_gpu": r["nvlink_gbs_per_gpu"], "frac_of_peer_copy_770": r["frac"],
+            "hbm_gbs_written_per_gpu": r["hbm_gbs_written_per_gpu"]}
+
+
+def measure_sweep(rank, world, device, local_rank, peak, workloads=("ck2", "pa4"), max_envs=1048576):
+    """BASELINE configs[4]: batch sweep 256 ... 1 048 576 envs per GPU, fused 33-step launches and
+    chained per-step launches, whole-job numbers at this world size."""
+    lines = []
+    for wl in workloads:
+        spec = workload_spec(wl)
+        B = 256
+        while B <= max_envs:
+            K = 330 if B <= 262144 else 99
+            r = measure_workload(spec, wl, B, K, 33, rank, world, device, local_rank, peak, modes=("fused", "per_step_chained"),
+                                 sample_clocks=False)
+            line = {"workload": wl, "envs_per_gpu": B, "n_gpus": world}
+            for k in ("fused", "per_step_chained"):
+                if k in r:
+                    line[k] = {x: r[k][x] for x in ("value", "us_per_step", "achieved_gbs", "frac")}
+            lines.append(line)
+            B *= 4
+    return lines
+
+
+def measure_extras(env, spec, args, peak, mode="fused", world=1, rank=0, device="cuda:0", local_rank=0, ring=MAX_STEPS):
+    """Everything beside the headline, measured by the same timed_steps(): all ranks call this."""
     import torch
     extra = {}
     B, N = env.B, env.N
-    bpe = bytes_per_env_step(env)
-    if mode == "fused":
-        # (0) the same workload as one launch PER STEP (what a policy in the loop needs)
-        runner = StepRunner(env, spec, ring, SEED)
-        runner.capture()
-        K = max(ring, args.steps // ring * ring)
-        ms, _ = timed_steps(runner, K, ring, 1, device, local_rank, sample_clocks=False)
-        ach = bpe * B * K / (ms * 1e-3) / 1e9
-        extra["per_step_launches"] = {"value": B * N * K / (ms * 1e-3), "unit": UNIT, "launches": K,
-                                      "us_per_step": ms * 1e3 / K, "achieved_gbs": ach, "frac": ach / peak,
-                                      "algorithmic_bytes_per_env_step": bpe, "rollout_ring_slots": ring,
-                                      "note": "one launch per step from a CUDA graph with programmatic dependent launch; outputs to a %d-slot ring of %.0f MB (> L2); this GPU only" % (ring, ring * bpe * B / 1e6)}
-        del runner
-    # (1) fused T-step rollout kernel: state in registers, Philox actions, one launch per 33 steps
+    K = max(args.steps, 330)
+    peak_src = hbm_peak()[1]
+    # (0) this workload, one launch PER STEP (what a policy in the loop needs)
+    r = measure_workload(spec, args.workload, B, K, 33, rank, world, device, local_rank, peak, modes=("step",))
+    extra["per_step_launches"] = dict(r["per_step_chained"], note="one cm3_*_step_chained launch per step from a CUDA graph: tile i of step k+1 waits only for tile i of step k (ticket words), so the store phase of a step overlaps the compute phase of the next; outputs to a rollout ring > L2")
+    extra["per_step_stream_ordered"] = dict(r["per_step_stream_ordered"], note="round 1's per-step mode: plain stream order + programmatic dependent launch (griddepcontrol.wait on the whole previous grid)")
+    # (1) fused T-step rollout kernel with device Philox actions
     T = MAX_STEPS
-    out = env.alloc_outputs(T)
-    for _ in range(3):
-        env.rollout(T, actions=None, seed=SEED, auto_reset=True, out=out)
-    reps = max(3, min(30, args.steps // T))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for r in range(reps):
-        env.rollout(T, actions=None, seed=SEED, t0=r * T, auto_reset=True, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    out_bytes = env.out_bytes_per_env_step()
-    state_bytes = bpe - out_bytes - N
-    fused_bpe = out_bytes + state_bytes / T  # actions come from Philox: no action bytes
-    ach = fused_bpe * B * T * reps / (ms * 1e-3) / 1e9
-    extra["fused_rollout_T33_philox"] = {"value": B * N * T * reps / (ms * 1e-3), "unit": UNIT, "launches": reps,
-                                  "ms_per_launch": ms / reps, "achieved_gbs": ach, "frac": ach / peak,
-                                  "algorithmic_bytes_per_env_step": fused_bpe,
-                                  "note": "one launch = 33 env steps, device Philox actions, in-kernel reset, outputs to a [33][B] rollout buffer (%.0f MB > L2)" % (out_bytes * B * T / 1e6)}
+    out = env.alloc_outputs(T, fields=ref_fields(env))
+    plan = env.plan_rollout(T, actions=None, out=out, auto_reset=True, seed=SEED)
+
+    class _P(object):
+        launches = 0
+
+        def run(self, k):
+            for i in range(k // T):
+                plan(self.launches * T)
+                self.launches += 1
+    reps = max(3, min(30, K // T))
+    ms, _, _ = timed_steps(_P(), reps * T, 3 * T, world, device, local_rank, sample_clocks=False)
+    fb = fused_bytes(env, spec, T, with_actions=False)
+    ach = fb * B * T * reps / (ms * 1e-3) / 1e9
+    extra["fused_rollout_T33_philox"] = {"value": world * B * N * T * reps / (ms * 1e-3), "unit": UNIT, "launches": reps,
+                                         "ms_per_launch": ms / reps, "achieved_gbs": ach, "frac": ach / peak,
+                                         "algorithmic_bytes_per_env_step": fb,
+                                         "note": "one launch = 33 env steps, device Philox actions, in-kernel reset"}
+    del out, plan
+    torch.cuda.empty_cache()
+    # (2) the other env family and the other configs named by BASELINE.json, same batch per GPU
+    others = [w for w in ("ck2", "pa4", "pa3", "pm2", "ck1") if w != args.workload]
+    extra["workloads"] = {}
+    for wl in others:
+        extra["workloads"][wl] = measure_workload(workload_spec(wl), wl, B, K, 33, rank, world, device, local_rank, peak,
+                                                  modes=("fused", "per_step_chained"))
+    # (3) configs[3]: PM2 rollout all-gather (32 768 envs per GPU), by NCCL and by the kernel's own peer stores
+    if world > 1:
+        for m in ("nccl", "peer"):
+            extra["gather_pm2_%s" % m] = measure_gather("pm2", 32768, m, rank, world, device, local_rank, peak, peak_src)
+        extra["gather_pm2_peer_no_overlap"] = measure_gather("pm2", 32768, "peer", rank, world, device, local_rank, peak, peak_src, overlap=False)
+    # (4) configs[4]: batch sweep at this world size
+    if not args.no_sweep:
+        extra["sweep"] = measure_sweep(rank, world, device, local_rank, peak)
+    # (5) B = 1 drop-in latency
+    if rank == 0:
+        extra["dropin_b1"] = measure_dropin_latency(device)
     return extra
 
 
@@ -542,10 +802,8 @@ def run_reference(args):
     rng = np.random.default_rng(SEED)
     actions = rng.integers(0, 5, size=(MAX_STEPS, Bs, spec["n"])).astype(np.int32)
     budget_s = 120.0
-    t_probe = time.perf_counter()
     for t in range(W):
         env.step(actions[t % MAX_STEPS])
-    per_step = (time.perf_counter() - t_probe) / W
     reset()
     t0 = time.perf_counter()
     done_steps = 0
@@ -558,13 +816,19 @@ def run_reference(args):
             break
     el = time.perf_counter() - t0
     value = Bs * spec["n"] * done_steps / el
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     sample = "%d envs per step (of the %d-env workload) x %d steps, %d threads (OpenMP over envs), caller-side reset every 33 steps" % (Bs, args.envs, done_steps, nthreads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": done_steps, "warmup": W,
+        "n_gpus": world, "steps": done_steps, "warmup": W,
         "ms_per_step": el * 1e3 / done_steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": spec["label"] % args.envs, "sample": sample},
+        # same keys as the GPU arm's config (the driver compares them)
+        "config": {"workload": spec["label"] % args.envs, "envs_per_gpu": args.envs, "n_agents": spec["n"], "mode": "cpu",
+                   "actions": "uniform int in 0..4, a [33][B][N] stream pre-generated in host memory and read by every step",
+                   "auto_reset": True, "parallelism": "OpenMP over envs, %d host threads, one process" % nthreads,
+                   "timing": "time.perf_counter around the timed steps", "launch": "one C call per step",
+                   "l2": "n/a", "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -579,13 +843,15 @@ def main():
     ap.add_argument("--impl", default="cm3_b200", choices=["cm3_b200", "reference"])
     ap.add_argument("--workload", default="ck2")
     ap.add_argument("--envs", type=int, default=B_PER_GPU, help="env instances per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=99)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="--gather: single symmetric buffer, no overlap of rollout k+1 with the drain of k")
     ap.add_argument("--ref-envs", type=int, default=0,
                     help="--impl reference: envs per step (0 = the full --envs batch; a smaller sample stays L3-resident)")
-    ap.add_argument("--mode", default="fused", choices=["fused", "step"],
-                    help="fused: one launch per 33-step episode (headline); step: one launch per step")
+    ap.add_argument("--mode", default="fused", choices=["fused", "step", "step_ordered"],
+                    help="fused: one launch per 33-step episode (headline); step: one chained launch per step; step_ordered: round 1's stream-ordered per-step launches")
     ap.add_argument("--gather", default="none", choices=["none", "nccl", "peer", "auto"],
                     help="all-gather the rollout buffers to every GPU (BASELINE.json configs[3])")
     args = ap.parse_args()

@@ -4,7 +4,8 @@ import os
 
 from .build import library_path
 
-MAX_AGENTS = 4
+MAX_AGENTS = 8
+ABI_VERSION = 2
 MAX_DST = 8
 REAL_F32, REAL_F64 = 0, 1
 TILE_REAL, TILE_I8 = 0, 1
@@ -24,16 +25,18 @@ class CheckersConfig(C.Structure):
                 ("n_agents", C.c_int32), ("max_steps", C.c_int32),
                 ("agents_r", C.c_int32 * MAX_AGENTS), ("agents_c", C.c_int32 * MAX_AGENTS),
                 ("num_envs", C.c_int32), ("real", C.c_int32), ("device", C.c_int32),
-                ("tile", C.c_int32), ("env_id_offset", C.c_int64)]
+                ("tile", C.c_int32), ("env_id_offset", C.c_int64),
+                ("random_goal", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CheckersState(C.Structure):
-    _fields_ = [("remaining", C.c_void_p), ("agents", C.c_void_p), ("meta", C.c_void_p)]
+    _fields_ = [("remaining", C.c_void_p), ("agents", C.c_void_p), ("meta", C.c_void_p),
+                ("sync", C.c_void_p)]
 
 
 class CheckersOutputs(C.Structure):
     FIELDS = ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "reward", "local_rewards",
-              "done")
+              "done", "goal_idx")
     _fields_ = [(f, C.c_void_p) for f in FIELDS]
 
 
@@ -51,11 +54,11 @@ class ParticleConfig(C.Structure):
 
 class ParticleState(C.Structure):
     _fields_ = [("sv", C.c_void_p), ("landmarks", C.c_void_p), ("steps", C.c_void_p),
-                ("collisions", C.c_void_p), ("reached", C.c_void_p)]
+                ("collisions", C.c_void_p), ("reached", C.c_void_p), ("sync", C.c_void_p)]
 
 
 class ParticleOutputs(C.Structure):
-    FIELDS = ("global_state", "obs_others", "obs_self", "reward", "reward_n", "done")
+    FIELDS = ("global_state", "obs_others", "obs_self", "reward", "reward_n", "done", "collisions", "reached")
     _fields_ = [(f, C.c_void_p) for f in FIELDS]
 
 
@@ -67,6 +70,9 @@ SYMBOLS = {
     "cm3_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "cm3_checkers_create": (C.c_int, [C.POINTER(CheckersConfig), C.POINTER(_vp)]),
     "cm3_checkers_destroy": (C.c_int, [_vp]),
+    "cm3_checkers_tiles": (C.c_int, [_vp, C.POINTER(_i32)]),
+    "cm3_checkers_step_chained": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _u64, _i64, _i32,
+                                            C.POINTER(CheckersOutputs), _vp]),
     "cm3_checkers_reset": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
                                      C.POINTER(CheckersOutputs), _vp]),
     "cm3_checkers_step": (C.c_int, [_vp, C.POINTER(CheckersState), _vp,
@@ -83,9 +89,18 @@ SYMBOLS = {
     "cm3_checkers_set_state": (C.c_int, [_vp, C.POINTER(CheckersState), C.POINTER(CheckersState), _vp]),
     "cm3_checkers_step_host_packed": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp,
                                                 C.POINTER(CheckersOutputs), _vp, _vp, C.c_size_t, _vp]),
+    "cm3_checkers_rollout_host": (C.c_int, [_vp, C.POINTER(CheckersState), _vp, _vp, _i32, _u64, _i64, _i32,
+                                            C.POINTER(CheckersOutputs), C.POINTER(_vp), _vp, C.c_size_t,
+                                            C.c_size_t, _vp]),
+    "cm3_particle_rollout_host": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp, _i32, _u64, _i64, _i32,
+                                            C.POINTER(ParticleOutputs), C.POINTER(_vp), _vp, C.c_size_t,
+                                            C.c_size_t, _vp]),
     "cm3_particle_default_config": (None, [C.POINTER(ParticleConfig), _i32, _i32]),
     "cm3_particle_create": (C.c_int, [C.POINTER(ParticleConfig), C.POINTER(_vp)]),
     "cm3_particle_destroy": (C.c_int, [_vp]),
+    "cm3_particle_tiles": (C.c_int, [_vp, C.POINTER(_i32)]),
+    "cm3_particle_step_chained": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _u64, _i64, _i32,
+                                            C.POINTER(ParticleOutputs), _vp]),
     "cm3_particle_reset": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp, _vp, _u64, _i64,
                                      C.POINTER(ParticleOutputs), _vp]),
     "cm3_particle_step": (C.c_int, [_vp, C.POINTER(ParticleState), _vp,
@@ -121,8 +136,8 @@ def load_library():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.cm3_abi_version() != 1:
-        raise Cm3Error(-1, "ABI version mismatch: library %d, binding 1" % lib.cm3_abi_version())
+    if lib.cm3_abi_version() != ABI_VERSION:
+        raise Cm3Error(-1, "ABI version mismatch: library %d, binding %d" % (lib.cm3_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

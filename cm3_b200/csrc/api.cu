@@ -72,6 +72,14 @@ bool full_enabled() {
     return on;
 }
 
+bool dyn_geometry_forced() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_CK_DYNAMIC");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+
 bool tma_enabled() {
     static const bool on = [] {
         const char *v = getenv("CM3_TMA");
@@ -113,13 +121,65 @@ static int check_fields_in_block(const FieldCopy *cp, int n, const void *dev_blo
 
 using namespace cm3;
 
+// copy stream + events of *_rollout_host (created on first use, on the handle's device)
+struct HostPipe {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t stepped[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    bool ready = false;
+    int init() {
+        if (ready) return CM3_OK;
+        CM3_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CM3_CUDA(cudaEventCreateWithFlags(&stepped[i], cudaEventDisableTiming));
+            CM3_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return CM3_OK;
+    }
+    void destroy() {
+        if (copy) cudaStreamDestroy(copy);
+        for (int i = 0; i < 2; ++i) {
+            if (stepped[i]) cudaEventDestroy(stepped[i]);
+            if (copied[i]) cudaEventDestroy(copied[i]);
+        }
+        copy = nullptr; ready = false;
+    }
+};
+
+// The double-buffered host rollout shared by both games: step(t, slot) enqueues the kernel of step t
+// writing output set `slot` on the compute stream.
+template <typename StepFn>
+static int rollout_host_loop(HostPipe &hp, const int8_t *actions_host, int8_t *actions_dev, size_t act_bytes, int T,
+                             const void *const *dev_blocks, void *host_blocks, size_t block_bytes, size_t host_stride,
+                             cudaStream_t s, StepFn step) {
+    int rc = hp.init();
+    if (rc != CM3_OK) return rc;
+    for (int t = 0; t < T; ++t) {
+        const int slot = t & 1;
+        if (t >= 2) CM3_CUDA(cudaStreamWaitEvent(s, hp.copied[slot], 0));  // set `slot` has left the device
+        CM3_CUDA(cudaMemcpyAsync(actions_dev + (size_t)slot * act_bytes, actions_host + (size_t)t * act_bytes, act_bytes,
+                                 cudaMemcpyHostToDevice, s));
+        if ((rc = step(t, slot)) != CM3_OK) return rc;
+        CM3_CUDA(cudaEventRecord(hp.stepped[slot], s));
+        CM3_CUDA(cudaStreamWaitEvent(hp.copy, hp.stepped[slot], 0));
+        CM3_CUDA(cudaMemcpyAsync((char *)host_blocks + (size_t)t * host_stride, dev_blocks[slot], block_bytes,
+                                 cudaMemcpyDeviceToHost, hp.copy));
+        CM3_CUDA(cudaEventRecord(hp.copied[slot], hp.copy));
+    }
+    CM3_CUDA(cudaStreamSynchronize(hp.copy));
+    CM3_CUDA(cudaStreamSynchronize(s));
+    return CM3_OK;
+}
+
 struct cm3_checkers_s {
     cm3_checkers_config cfg;
     CkParams base;  // geometry-derived constants, pointers zero
+    HostPipe pipe;
 };
 struct cm3_particle_s {
     cm3_particle_config cfg;
     PtParams base;
+    HostPipe pipe;
 };
 
 // the kernels read an env's N action bytes as one word (common.cuh: load_actions_packed)
@@ -134,7 +194,7 @@ static int check_actions_alignment(const int8_t *actions, int N) {
 
 static CkOut ck_out(const cm3_checkers_outputs &o) {
     return CkOut{(char *)o.grid, (char *)o.vec, (char *)o.obs_others, (char *)o.obs_self_t, (char *)o.obs_self_v,
-                 (char *)o.reward, (char *)o.local_rewards, o.done};
+                 (char *)o.reward, (char *)o.local_rewards, o.done, o.goal_idx};
 }
 
 // rollout_gather: n_dst destination sets with identical NULL patterns, this shard at rows
@@ -167,7 +227,7 @@ static int fill_destinations(int32_t n_dst, const Out *dsts, int64_t dst_B, int6
 
 static PtOut pt_out(const cm3_particle_outputs &o) {
     return PtOut{(char *)o.global_state, (char *)o.obs_others, (char *)o.obs_self, (char *)o.reward,
-                 (char *)o.reward_n, o.done};
+                 (char *)o.reward_n, o.done, o.collisions, o.reached};
 }
 
 extern "C" {
@@ -206,8 +266,14 @@ int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out) {
         return CM3_ERR_UNSUPPORTED;
     }
     if (N > CM3_MAX_AGENTS || !checkers_geometry_supported(R, C, O, N)) {
-        set_error("no compiled Checkers kernel for n_rows=%d n_columns=%d n_obs=%d n_agents=%d", R, C, O, N);
+        set_error("n_rows=%d n_columns=%d n_obs=%d n_agents=%d is outside what the bitboards address "
+                  "(n_rows*n_columns <= 64, n_columns + 2 n_obs + 1 <= 32, n_obs <= 3, n_agents <= %d)", R, C, O, N, CM3_MAX_AGENTS);
         return CM3_ERR_UNSUPPORTED;
+    }
+    if (cfg->random_goal != 0 && cfg->random_goal != 1) { set_error("random_goal must be 0 or 1"); return CM3_ERR_BAD_ARG; }
+    if (cfg->random_goal && N != 1) {
+        set_error("random_goal is the stage-1 (n_agents == 1) episode protocol (train_offpolicy.py:291-296)");
+        return CM3_ERR_BAD_ARG;
     }
     if (N == 1 && R < 3) {  // checkers.py:276 starts the agent on row 2
         set_error("n_agents == 1 needs n_rows >= 3 (checkers.py:276)");
@@ -237,6 +303,10 @@ int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out) {
     p.B = cfg->num_envs;
     p.max_steps = cfg->max_steps;
     p.env_id_offset = cfg->env_id_offset;
+    p.R = R; p.C = C; p.O = O;
+    p.random_goal = cfg->random_goal;
+    for (int i = 0; i < R; ++i)  // cells (i,j) with (i+j) even are green, odd orange (checkers.py:54-63)
+        for (int j = 0; j < C; ++j) p.color_mask[(i + j) & 1] |= 1ull << (i * C + j);
     const int TR = R + 2 * O, TC = C + 2 * O + 1;  // checkers.py:24-25
     for (int i = 0; i < N; ++i) {
         p.start_r[i] = cfg->agents_r[i] + O;  // checkers.py:34-35
@@ -254,7 +324,15 @@ int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out) {
 
 int cm3_checkers_destroy(cm3_checkers_t h) {
     if (!h) { set_error("handle is NULL"); return CM3_ERR_BAD_ARG; }
+    if (h->pipe.ready) { DeviceGuard g(h->cfg.device); h->pipe.destroy(); }
     delete h;
+    return CM3_OK;
+}
+
+int cm3_checkers_tiles(cm3_checkers_t h, int32_t *tiles) {
+    if (!h || !tiles) { set_error("handle/tiles is NULL"); return CM3_ERR_BAD_ARG; }
+    const int ew = checkers_tile_envs(h->cfg.n_agents);
+    *tiles = (h->cfg.num_envs + ew - 1) / ew;
     return CM3_OK;
 }
 
@@ -265,7 +343,7 @@ static int ck_fill(cm3_checkers_t h, const cm3_checkers_state *st, const cm3_che
         return CM3_ERR_BAD_ARG;
     }
     p = h->base;
-    p.remaining = st->remaining; p.agents = st->agents; p.meta = st->meta;
+    p.remaining = st->remaining; p.agents = st->agents; p.meta = st->meta; p.sync = st->sync;
     p.n_dst = 1; p.out_B = p.B; p.out_env0 = 0;
     if (outs) p.out[0] = ck_out(*outs);
     return CM3_OK;
@@ -326,6 +404,20 @@ int cm3_checkers_step(cm3_checkers_t h, const cm3_checkers_state *st, const int8
     return cm3_checkers_rollout(h, st, actions, 0, 0, 1, 0, nullptr, outs, stream);
 }
 
+int cm3_checkers_step_chained(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                              uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_checkers_outputs *outs, void *stream) {
+    if (!actions) { set_error("actions is NULL"); return CM3_ERR_BAD_ARG; }
+    CkParams p;
+    int rc = ck_fill(h, st, outs, p);
+    if (rc != CM3_OK) return rc;
+    if (!st->sync) { set_error("step_chained needs state.sync (the per-tile chaining words)"); return CM3_ERR_BAD_ARG; }
+    if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
+    p.mode = 0; p.T = 1; p.auto_reset = auto_reset ? 1 : 0; p.chained = 1;
+    p.actions = actions; p.seed = seed; p.t0 = t0;
+    return ck_launch(h, p, stream);
+}
+
 static int ck_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
                         int8_t *actions_dev, const cm3_checkers_outputs *od, const cm3_checkers_outputs *oh,
                         const void *dev_block, void *host_block, size_t block_bytes, void *stream) {
@@ -350,6 +442,7 @@ static int ck_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const in
         {oh->reward, od->reward, B * rs},
         {oh->local_rewards, od->local_rewards, B * N * rs},
         {oh->done, od->done, B},
+        {oh->goal_idx, od->goal_idx, B * N},
     };
     const int n = (int)(sizeof(cp) / sizeof(cp[0]));
     int rc;
@@ -374,6 +467,25 @@ int cm3_checkers_step_host_packed(cm3_checkers_t h, const cm3_checkers_state *st
                                   void *host_block, size_t block_bytes, void *stream) {
     if (!dev_block || !host_block) { set_error("dev_block/host_block is NULL"); return CM3_ERR_BAD_ARG; }
     return ck_step_host(h, st, actions_host, actions_dev, od, nullptr, dev_block, host_block, block_bytes, stream);
+}
+
+int cm3_checkers_rollout_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
+                              int8_t *actions_dev, int32_t T, uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_checkers_outputs *outs_dev, const void *const *dev_blocks,
+                              void *host_blocks, size_t block_bytes, size_t host_stride, void *stream) {
+    if (!h || !actions_host || !actions_dev || !outs_dev || !dev_blocks || !dev_blocks[0] || !dev_blocks[1] || !host_blocks) {
+        set_error("handle/actions/outputs/blocks pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    if (T < 1 || host_stride < block_bytes) { set_error("T must be >= 1 and host_stride >= block_bytes"); return CM3_ERR_BAD_ARG; }
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    const size_t act_bytes = (size_t)h->cfg.num_envs * h->cfg.n_agents;
+    return rollout_host_loop(h->pipe, actions_host, actions_dev, act_bytes, T, dev_blocks, host_blocks, block_bytes,
+                             host_stride, (cudaStream_t)stream, [&](int t, int slot) {
+                                 return cm3_checkers_rollout(h, st, actions_dev + (size_t)slot * act_bytes, seed, t0 + t, 1,
+                                                             auto_reset, nullptr, &outs_dev[slot], stream);
+                             });
 }
 
 static int ck_state_copy(cm3_checkers_t h, const cm3_checkers_state *dev, const cm3_checkers_state *host,
@@ -432,7 +544,7 @@ int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
         return CM3_ERR_BAD_ARG;
     }
     if (cfg->n_agents > CM3_MAX_AGENTS) {
-        set_error("no compiled particle kernel for n_agents=%d (1..%d supported)", cfg->n_agents, CM3_MAX_AGENTS);
+        set_error("n_agents=%d: the particle kernels keep 1..%d agents per env in registers", cfg->n_agents, CM3_MAX_AGENTS);
         return CM3_ERR_UNSUPPORTED;
     }
     int st = require_device(cfg->device);
@@ -446,6 +558,7 @@ int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
     p.dt = cfg->dt; p.damping = cfg->damping; p.contact_force = cfg->contact_force;
     p.contact_margin = cfg->contact_margin;
     p.dist_min = cfg->agent_size + cfg->agent_size;  // core.py:189 / multi-goal_spread.py:117
+    p.dist_min2 = p.dist_min * p.dist_min;
     p.mass = cfg->mass; p.sensitivity = cfg->sensitivity; p.reach_thresh = cfg->reach_thresh;
     for (int i = 0; i < CM3_MAX_AGENTS; ++i) {
         p.agents_x[i] = cfg->agents_x[i]; p.agents_y[i] = cfg->agents_y[i];
@@ -474,7 +587,14 @@ int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
 
 int cm3_particle_destroy(cm3_particle_t h) {
     if (!h) { set_error("handle is NULL"); return CM3_ERR_BAD_ARG; }
+    if (h->pipe.ready) { DeviceGuard g(h->cfg.device); h->pipe.destroy(); }
     delete h;
+    return CM3_OK;
+}
+
+int cm3_particle_tiles(cm3_particle_t h, int32_t *tiles) {
+    if (!h || !tiles) { set_error("handle/tiles is NULL"); return CM3_ERR_BAD_ARG; }
+    *tiles = (h->cfg.num_envs + kWarp - 1) / kWarp;
     return CM3_OK;
 }
 
@@ -486,7 +606,7 @@ static int pt_fill(cm3_particle_t h, const cm3_particle_state *st, const cm3_par
     }
     p = h->base;
     p.sv = (char *)st->sv; p.landmarks = (char *)st->landmarks;
-    p.steps = st->steps; p.collisions = st->collisions; p.reached = st->reached;
+    p.steps = st->steps; p.collisions = st->collisions; p.reached = st->reached; p.sync = st->sync;
     p.n_dst = 1; p.out_B = p.B; p.out_env0 = 0;
     if (outs) p.out[0] = pt_out(*outs);
     return CM3_OK;
@@ -511,7 +631,7 @@ int cm3_particle_reset(cm3_particle_t h, const cm3_particle_state *st, const voi
     p.mode = 1; p.T = 1;
     p.init_pos = (const char *)init_pos; p.init_landmarks = (const char *)init_landmarks;
     p.env_mask = env_mask; p.seed = seed; p.reset_counter = reset_counter;
-    p.out[0].reward = nullptr; p.out[0].reward_n = nullptr;
+    p.out[0].reward = nullptr; p.out[0].reward_n = nullptr; p.out[0].collisions = nullptr; p.out[0].reached = nullptr;
     return pt_launch(h, p, stream);
 }
 
@@ -550,6 +670,20 @@ int cm3_particle_step(cm3_particle_t h, const cm3_particle_state *st, const int8
     return cm3_particle_rollout(h, st, actions, 0, 0, 1, 0, nullptr, outs, stream);
 }
 
+int cm3_particle_step_chained(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                              uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_particle_outputs *outs, void *stream) {
+    if (!actions) { set_error("actions is NULL"); return CM3_ERR_BAD_ARG; }
+    PtParams p;
+    int rc = pt_fill(h, st, outs, p);
+    if (rc != CM3_OK) return rc;
+    if (!st->sync) { set_error("step_chained needs state.sync (the per-tile chaining words)"); return CM3_ERR_BAD_ARG; }
+    if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
+    p.mode = 0; p.T = 1; p.auto_reset = auto_reset ? 1 : 0; p.chained = 1;
+    p.actions = actions; p.seed = seed; p.t0 = t0;
+    return pt_launch(h, p, stream);
+}
+
 static int pt_step_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
                         int8_t *actions_dev, const cm3_particle_outputs *od, const cm3_particle_outputs *oh,
                         const void *dev_block, void *host_block, size_t block_bytes, void *stream) {
@@ -571,6 +705,8 @@ static int pt_step_host(cm3_particle_t h, const cm3_particle_state *st, const in
         {oh->reward, od->reward, B * rs},
         {oh->reward_n, od->reward_n, B * N * rs},
         {oh->done, od->done, B},
+        {oh->collisions, od->collisions, B * 4},
+        {oh->reached, od->reached, B},
     };
     const int n = (int)(sizeof(cp) / sizeof(cp[0]));
     int rc;
@@ -595,6 +731,25 @@ int cm3_particle_step_host_packed(cm3_particle_t h, const cm3_particle_state *st
                                   void *host_block, size_t block_bytes, void *stream) {
     if (!dev_block || !host_block) { set_error("dev_block/host_block is NULL"); return CM3_ERR_BAD_ARG; }
     return pt_step_host(h, st, actions_host, actions_dev, od, nullptr, dev_block, host_block, block_bytes, stream);
+}
+
+int cm3_particle_rollout_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
+                              int8_t *actions_dev, int32_t T, uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_particle_outputs *outs_dev, const void *const *dev_blocks,
+                              void *host_blocks, size_t block_bytes, size_t host_stride, void *stream) {
+    if (!h || !actions_host || !actions_dev || !outs_dev || !dev_blocks || !dev_blocks[0] || !dev_blocks[1] || !host_blocks) {
+        set_error("handle/actions/outputs/blocks pointer is NULL");
+        return CM3_ERR_BAD_ARG;
+    }
+    if (T < 1 || host_stride < block_bytes) { set_error("T must be >= 1 and host_stride >= block_bytes"); return CM3_ERR_BAD_ARG; }
+    DeviceGuard g(h->cfg.device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    const size_t act_bytes = (size_t)h->cfg.num_envs * h->cfg.n_agents;
+    return rollout_host_loop(h->pipe, actions_host, actions_dev, act_bytes, T, dev_blocks, host_blocks, block_bytes,
+                             host_stride, (cudaStream_t)stream, [&](int t, int slot) {
+                                 return cm3_particle_rollout(h, st, actions_dev + (size_t)slot * act_bytes, seed, t0 + t, 1,
+                                                             auto_reset, nullptr, &outs_dev[slot], stream);
+                             });
 }
 
 static int pt_state_copy(cm3_particle_t h, const cm3_particle_state *dev, const cm3_particle_state *host,

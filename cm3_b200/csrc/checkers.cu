@@ -81,74 +81,122 @@ template <int N> __device__ __forceinline__ int pick(const int (&v)[N], int idx)
     return r;
 }
 
-// Real: type of the small vectors and rewards; Tile: element type of the two bulky outputs (the
-// per-agent window and the global grid) - Real, or int8_t for the compact encoding.
-template <int R, int C, int O, int N, typename Real, typename Tile = Real>
-struct CkGeom {
-    static constexpr int TR = R + 2 * O;
-    static constexpr int TC = C + 2 * O + 1;
-    static constexpr int W = 2 * O + 1;
-    static constexpr int WW3 = W * W * 3;
-    static constexpr int G = R * (C + 1) * 2;
-    static constexpr int L = 2 * (N > 1 ? N - 1 : 1);
-    static constexpr int NP = (N == 3) ? 4 : N;  // lanes reserved per env
-    static constexpr int EW = kWarp / NP;        // envs per warp
-    static constexpr int CNT = R * C / 2 + 1;
-    static constexpr int kWinBytes = round_up(EW * N * WW3 * (int)sizeof(Tile), 16);
-    static constexpr int kGridBytes = round_up(EW * G * (int)sizeof(Tile), 16);
-    static constexpr int kWarpStageBytes = kWinBytes + kGridBytes + ActionStream<N>::kSmemBytes;
-    static constexpr int kLutBytes = round_up((TR + TC + CNT) * (int)sizeof(Real), 128);
-    static constexpr int kSmemBytes = kLutBytes + kCkWarpsPerBlock * kWarpStageBytes;
-    static constexpr uint32_t CM = (C >= 32) ? 0xFFFFFFFFu : ((1u << C) - 1u);
-    static constexpr uint32_t kEven = 0x55555555u & CM;  // columns j with j even
-    static constexpr uint32_t kOdd = 0xAAAAAAAAu & CM;
-    static constexpr uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
-    static_assert(R % 2 == 1 && C % 2 == 0, "checkers.py:16-17");
-    static_assert(R * C <= 64 && TC <= 32 && TR <= kCkMaxTR && N >= 1 && N <= CM3_MAX_AGENTS, "geometry");
-    static_assert(W <= 8, "tri_pack holds 8 cells");
-
+// ---------------------------------------------------------------- board geometry
+// The kernel is written against a geometry provider.  StaticGeo compiles (n_rows, n_columns, n_obs)
+// in - every loop unrolls, every mask is an immediate - and exists for the boards of the reference's
+// configs; DynGeo reads them from the parameter block, so that ANY board the bitboards can address
+// runs (Checkers.__init__ takes the geometry as data, env/checkers.py:5-35).
+template <int R_, int C_, int O_>
+struct StaticGeo {
+    static constexpr bool kStatic = true;
+    __host__ __device__ StaticGeo() {}
+    __device__ __forceinline__ explicit StaticGeo(const CkParams &) {}
+    __host__ __device__ static constexpr int R() { return R_; }
+    __host__ __device__ static constexpr int C() { return C_; }
+    __host__ __device__ static constexpr int O() { return O_; }
     // cells (i,j) with (i+j) even are green, odd orange (checkers.py:54-63)
-    static __host__ __device__ constexpr uint64_t color_all(int color) {
+    __host__ __device__ static constexpr uint64_t color_const(int color) {
         uint64_t m = 0;
-        for (int i = 0; i < R; ++i)
-            for (int j = 0; j < C; ++j)
-                if (((i + j) & 1) == color) m |= 1ull << (i * C + j);
+        for (int i = 0; i < R_; ++i)
+            for (int j = 0; j < C_; ++j)
+                if (((i + j) & 1) == color) m |= 1ull << (i * C_ + j);
         return m;
     }
+    __device__ __forceinline__ uint64_t color_all(const CkParams &, int color) const {
+        return color ? color_const(1) : color_const(0);
+    }
+    static_assert(R_ % 2 == 1 && C_ % 2 == 0, "checkers.py:16-17");
+    static_assert(R_ * C_ <= 64 && C_ + 2 * O_ + 1 <= 32 && R_ + 2 * O_ <= kCkMaxTR && 2 * O_ + 1 <= 8, "geometry");
+};
+struct DynGeo {
+    static constexpr bool kStatic = false;
+    int r, c, o;
+    __device__ __forceinline__ explicit DynGeo(const CkParams &p) : r(p.R), c(p.C), o(p.O) {}
+    __host__ DynGeo(int r_, int c_, int o_) : r(r_), c(c_), o(o_) {}
+    __host__ __device__ __forceinline__ int R() const { return r; }
+    __host__ __device__ __forceinline__ int C() const { return c; }
+    __host__ __device__ __forceinline__ int O() const { return o; }
+    __device__ __forceinline__ uint64_t color_all(const CkParams &p, int color) const { return p.color_mask[color]; }
 };
 
-template <int R, int C, int O, int N, typename Real, typename Tile>
+// lanes reserved per env: one per agent, rounded up to a power of two - and TWO for a single agent
+// (the second lane expands the global grid while the first expands the window: twice the warps for
+// the stage-1 board, whose one-thread-per-env launch was latency-bound in round 1)
+__host__ __device__ constexpr int ck_lanes_per_env(int N) { return N <= 2 ? 2 : N <= 4 ? 4 : 8; }
+
+// Real: type of the small vectors and rewards; Tile: element type of the two bulky outputs (the
+// per-agent window and the global grid) - Real, or int8_t for the compact encoding.
+template <int N, typename Real, typename Tile>
+struct CkLayout {
+    static constexpr int L = 2 * (N > 1 ? N - 1 : 1);
+    static constexpr int NP = ck_lanes_per_env(N);
+    static constexpr int EW = kWarp / NP;  // envs per warp
+    template <class Geo> __host__ __device__ static int win_bytes(const Geo &g) {
+        const int W = 2 * g.O() + 1;
+        return round_up(EW * N * W * W * 3 * (int)sizeof(Tile), 16);
+    }
+    template <class Geo> __host__ __device__ static int grid_bytes(const Geo &g) {
+        return round_up(EW * g.R() * (g.C() + 1) * 2 * (int)sizeof(Tile), 16);
+    }
+    template <class Geo> __host__ __device__ static int lut_bytes(const Geo &g) {
+        const int TR = g.R() + 2 * g.O(), TC = g.C() + 2 * g.O() + 1, CNT = g.R() * g.C() / 2 + 1;
+        return round_up((TR + TC + CNT) * (int)sizeof(Real), 128);
+    }
+    template <class Geo> __host__ __device__ static int warp_stage_bytes(const Geo &g) {
+        return win_bytes(g) + grid_bytes(g) + ActionStream<N>::kSmemBytes;
+    }
+    template <class Geo> __host__ __device__ static int smem_bytes(const Geo &g) {
+        return lut_bytes(g) + kCkWarpsPerBlock * warp_stage_bytes(g);
+    }
+    static_assert(N >= 1 && N <= CM3_MAX_AGENTS, "agents");
+};
+
+constexpr uint32_t kTagGoal = 0x60A10000u;  // Philox stream tag of the stage-1 goal redraw
+
+template <class Geo, int N, typename Real, typename Tile>
 __global__ void __launch_bounds__(kCkWarpsPerBlock *kWarp)
 checkers_kernel(const __grid_constant__ CkParams p) {
-    using Gm = CkGeom<R, C, O, N, Real, Tile>;
-    constexpr int TR = Gm::TR, TC = Gm::TC, W = Gm::W, WW3 = Gm::WW3, G = Gm::G, L = Gm::L;
-    constexpr int EW = Gm::EW;
-    constexpr uint32_t CM = Gm::CM;
+    using Ly = CkLayout<N, Real, Tile>;
+    const Geo geo(p);
+    const int R = geo.R(), C = geo.C(), O = geo.O();
+    const int TR = R + 2 * O, TC = C + 2 * O + 1, W = 2 * O + 1, WW3 = W * W * 3, G = R * (C + 1) * 2;
+    const int CNT = R * C / 2 + 1;
+    constexpr int L = Ly::L, EW = Ly::EW;
+    const uint32_t CM = (C >= 32) ? 0xFFFFFFFFu : ((1u << C) - 1u);
+    const uint32_t kEven = 0x55555555u & CM, kOdd = 0xAAAAAAAAu & CM;  // columns j with j even / odd
+    const uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
 
-    pdl_launch_dependents();  // the next step's grid may become resident while this one drains
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * kCkWarpsPerBlock + warp;
+    // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
+    TileTicket ticket;
+    ticket.take(tile * EW < p.B ? p.sync : nullptr, tile, lane);
+    if (ticket.mine != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
+
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *lut_row = reinterpret_cast<Real *>(smem_raw);
     Real *lut_col = lut_row + TR;
     Real *lut_cnt = lut_col + TC;
     for (int i = threadIdx.x; i < TR; i += blockDim.x) lut_row[i] = (Real)p.norm_row[i];
     for (int i = threadIdx.x; i < TC; i += blockDim.x) lut_col[i] = (Real)p.norm_col[i];
-    for (int i = threadIdx.x; i < Gm::CNT; i += blockDim.x) lut_cnt[i] = (Real)p.norm_cnt[i];
+    for (int i = threadIdx.x; i < CNT; i += blockDim.x) lut_cnt[i] = (Real)p.norm_cnt[i];
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Tile *stage_win = reinterpret_cast<Tile *>(smem_raw + Gm::kLutBytes + warp * Gm::kWarpStageBytes);
-    Tile *stage_grid = reinterpret_cast<Tile *>(reinterpret_cast<unsigned char *>(stage_win) + Gm::kWinBytes);
+    const int win_bytes = Ly::win_bytes(geo), grid_bytes = Ly::grid_bytes(geo);
+    Tile *stage_win = reinterpret_cast<Tile *>(smem_raw + Ly::lut_bytes(geo) + warp * Ly::warp_stage_bytes(geo));
+    Tile *stage_grid = reinterpret_cast<Tile *>(reinterpret_cast<unsigned char *>(stage_win) + win_bytes);
 
-    const int tile = blockIdx.x * kCkWarpsPerBlock + warp;
     const int env0 = tile * EW;
     if (env0 >= p.B) return;  // warp-uniform; no block-level sync below this point
     const int a = lane / EW, e = lane % EW;  // agent-major: lanes [a*EW, (a+1)*EW) hold agent a
     const int env = env0 + e;
     const int nenv = min(EW, p.B - env0);
-    const bool valid = (a < N) && (e < nenv);
+    const bool live = e < nenv;            // this lane works for an env of the batch ...
+    const bool owner = live && (a < N);    // ... and owns agent a of it
     const size_t B = (size_t)p.B;
 
-    pdl_wait();  // state written by the previous launch is visible from here on
+    // the state this tile's previous launch wrote is visible from here on
+    if (p.chained) ticket.wait(lane); else pdl_wait();
 
     // ---- load compact state
     uint64_t rem = 0;
@@ -156,12 +204,12 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     uint32_t meta = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) { ar[i] = O; ac[i] = O + i; ng[i] = 0; no[i] = 0; }
-    if (valid) {
-        rem = p.remaining[env];
-        meta = p.meta[env];
+    if (live) {
+        rem = __ldcg(reinterpret_cast<const unsigned long long *>(p.remaining) + env);
+        meta = __ldcg(p.meta + env);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const uint32_t w = p.agents[(size_t)env * N + i];
+            const uint32_t w = __ldcg(p.agents + (size_t)env * N + i);
             ar[i] = w & 0xFF; ac[i] = (w >> 8) & 0xFF; ng[i] = (w >> 16) & 0xFF; no[i] = w >> 24;
         }
     }
@@ -169,7 +217,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     uint32_t goals = meta >> 24;
 
     auto reset_state = [&]() {
-        rem = Gm::kFull;
+        rem = kFull;
         steps = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -183,7 +231,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     // action rows: streamed through shared memory (multi-step launches on whole tiles, see
     // ActionStream), else loaded directly at the top of each step
     ActionStream<N> acts;
-    acts.init(reinterpret_cast<unsigned char *>(stage_grid) + Gm::kGridBytes, p.mode == kCkReset ? nullptr : p.actions, p.B,
+    acts.init(reinterpret_cast<unsigned char *>(stage_grid) + grid_bytes, p.mode == kCkReset ? nullptr : p.actions, p.B,
               env0, EW, nenv == EW, p.T, lane);
     uint32_t act_word = acts.on ? acts.begin(e) : 0u;
 
@@ -201,7 +249,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         }
         __syncwarp();
         // ---------------- window of agent a (get_obs, checkers.py:97-109)
-        if (o0.obs_self_t != nullptr && valid) {
+        if (o0.obs_self_t != nullptr && owner) {
             Tile *win = stage_win + (e * N + a) * WW3;
             const int sh = my_c - O;  // leftmost window column, >= 0
 #pragma unroll
@@ -210,7 +258,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 const int i = pr - O;          // valid-grid row
                 const bool inr = (unsigned)i < (unsigned)R;
                 const uint32_t rowrem = inr ? ((uint32_t)(rem >> (inr ? i * C : 0)) & CM) : 0u;
-                const uint32_t gmask = (i & 1) ? Gm::kOdd : Gm::kEven;
+                const uint32_t gmask = (i & 1) ? kOdd : kEven;
                 const uint32_t omask = CM & ~gmask;
                 uint32_t occ = 0;
 #pragma unroll
@@ -255,8 +303,9 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             }
             if (lane == 0) bulk_commit();
         }
-        // ---------------- global grid (get_valid_grid, :66-76): lane a writes channel a
-        if (o0.grid != nullptr && valid && a < 2) {
+        // ---------------- global grid (get_valid_grid, :66-76).  N > 1: lane a < 2 writes channel a;
+        // N == 1: the env's second lane writes both channels
+        if (o0.grid != nullptr && live && (N == 1 ? a == 1 : a < 2)) {
             Tile *gr = stage_grid + e * G;
 #pragma unroll
             for (int i = 0; i < R; ++i) {
@@ -265,7 +314,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 for (int ch = 0; ch < 2; ++ch) {
                     if (N > 1 && ch == 1) break;           // N > 1: one channel per lane
                     const int mych = (N > 1) ? a : ch;
-                    const uint32_t cmask = (((i & 1) ^ mych) ? Gm::kOdd : Gm::kEven);
+                    const uint32_t cmask = (((i & 1) ^ mych) ? kOdd : kEven);
                     const uint32_t neg = rowrem & cmask;
                     // columns in groups of 8 (tri_pack); column C (the start column) holds no reward
 #pragma unroll
@@ -299,7 +348,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         }
         if (acts.on) act_word = acts.hand_over(t, act_loaded, e);
         // ---------------- small per-agent vectors, straight from registers
-        if (valid) {
+        if (owner) {
             const size_t rec = (slot + env) * N + a;
             const int my_g = pick<N>(ng, a), my_o = pick<N>(no, a);
             for (int d = 0; d < p.n_dst; ++d) {
@@ -321,6 +370,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                         }
                     }
                 }
+                if (o.goal_idx != nullptr) o.goal_idx[rec] = (uint8_t)((goals >> a) & 1u);  // :235
             }
         }
     };
@@ -329,13 +379,12 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
         if (p.mode == kCkReset) {
-            sel = valid && (p.env_mask == nullptr || p.env_mask[env] != 0);
+            sel = live && (p.env_mask == nullptr || p.env_mask[env] != 0);
             if (sel) {
-                goals = 0;
+                if (p.goal_idx != nullptr) {  // NULL: the env keeps the goals it has
+                    goals = 0;
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const uint32_t g = p.goal_idx ? (p.goal_idx[(size_t)env * N + i] & 1u) : (uint32_t)(i & 1);
-                    goals |= g << i;
+                    for (int i = 0; i < N; ++i) goals |= (uint32_t)(p.goal_idx[(size_t)env * N + i] & 1u) << i;
                 }
                 reset_state();
             }
@@ -344,16 +393,20 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             int act[N];
             if (p.actions != nullptr) {
                 uint32_t w = act_word;  // picked up from the stream during the previous emit
-                if (!acts.on && valid) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
+                if (!acts.on && live) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
 #pragma unroll
                 for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
             } else {
-                const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env),
-                                                      (uint64_t)(p.t0 + t));
+                // one Philox block of 4 words per 4 agents
 #pragma unroll
-                for (int i = 0; i < N; ++i) act[i] = action_from_word(philox_word(w, i), 5);
+                for (int i0 = 0; i0 < N; i0 += 4) {
+                    const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env),
+                                                          (uint64_t)(p.t0 + t), i0 / 4);
+#pragma unroll
+                    for (int i = i0; i < N && i < i0 + 4; ++i) act[i] = action_from_word(philox_word(w, i - i0), 5);
+                }
             }
-            if (p.actions_out != nullptr && valid)
+            if (p.actions_out != nullptr && owner)
                 p.actions_out[((size_t)t * B + env) * N + a] = (int8_t)pick<N>(act, a);
 
             // ---- agents act and collect strictly in index order (checkers.py:233-237)
@@ -390,12 +443,12 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             steps = (steps + 1) & 0xFFFFFF;  // :244
             bool done;                       // :246-260
             if (N == 1) {
-                const uint64_t mine = (goals & 1) ? Gm::color_all(1) : Gm::color_all(0);
+                const uint64_t mine = geo.color_all(p, (int)(goals & 1));
                 done = (steps == p.max_steps) || ((rem & mine) == 0ull);
             } else {
                 done = (steps == p.max_steps) || (rem == 0ull);
             }
-            if (valid) {
+            if (owner) {
                 double mine = rew[0];
 #pragma unroll
                 for (int i = 1; i < N; ++i) mine = (a == i) ? rew[i] : mine;
@@ -409,14 +462,23 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                     }
                 }
             }
-            if (p.auto_reset && done) reset_state();
+            if (p.auto_reset && done) {
+                if (N == 1 && p.random_goal) {  // a fresh goal per episode, train_offpolicy.py:291-296
+                    const unsigned long long genv = (unsigned long long)(p.env_id_offset + env), ctr = (unsigned long long)(p.t0 + t + 1);
+                    const Philox4 w = philox4x32_10((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)ctr,
+                                                    kTagGoal | ((uint32_t)(ctr >> 32) & 0xFFFFu), (uint32_t)p.seed,
+                                                    (uint32_t)(p.seed >> 32));
+                    goals = w.x >> 31;
+                }
+                reset_state();
+            }
         }
         emit(t);
         if (sel && a == 0 && o0.done != nullptr) o0.done[oe0 + env] = 0;  // checkers.py:291
     }
 
     // ---- store compact state
-    if (valid && a == 0) {
+    if (live && a == 0) {
         p.remaining[env] = rem;
         p.meta[env] = (uint32_t)steps | (goals << 24);
 #pragma unroll
@@ -424,67 +486,82 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             p.agents[(size_t)env * N + i] =
                 (uint32_t)ar[i] | ((uint32_t)ac[i] << 8) | ((uint32_t)ng[i] << 16) | ((uint32_t)no[i] << 24);
     }
+    ticket.publish(lane);  // this tile's next launch may go ahead
     // smem must outlive the async reads; the global writes themselves complete with the grid
     if (pending && lane < 2) bulk_wait_read();
 }
 
 // ------------------------------------------------------------------------ host side
 
-template <int R, int C, int O, int N, typename Real, typename Tile>
-static int launch_ck(const CkParams &p, cudaStream_t stream) {
-    using Gm = CkGeom<R, C, O, N, Real, Tile>;
-    auto kern = checkers_kernel<R, C, O, N, Real, Tile>;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    CM3_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::kSmemBytes));
-        attr_set[dev] = true;
+constexpr int kCkDynSmemMax = 160 * 1024;  // ceiling requested once for the geometry-as-data kernels
+
+template <class Geo, int N, typename Real, typename Tile>
+static int launch_ck(const Geo &geo, const CkParams &p, cudaStream_t stream) {
+    using Ly = CkLayout<N, Real, Tile>;
+    auto kern = checkers_kernel<Geo, N, Real, Tile>;
+    static std::atomic<uint64_t> attr_done{0};
+    const int smem = Ly::smem_bytes(geo);
+    if (smem > kCkDynSmemMax) {
+        set_error("board needs %d bytes of staging per block (limit %d)", smem, kCkDynSmemMax);
+        return CM3_ERR_UNSUPPORTED;
     }
-    const int ntiles = (p.B + Gm::EW - 1) / Gm::EW;
+    CM3_CUDA(ensure_smem_attr(kern, Geo::kStatic ? smem : kCkDynSmemMax, attr_done));
+    const int ntiles = (p.B + Ly::EW - 1) / Ly::EW;
     const int nblocks = (ntiles + kCkWarpsPerBlock - 1) / kCkWarpsPerBlock;
-    CM3_CUDA(launch_kernel(kern, nblocks, kCkWarpsPerBlock * kWarp, Gm::kSmemBytes, stream, pdl_enabled(), p));
+    CM3_CUDA(launch_kernel(kern, nblocks, kCkWarpsPerBlock * kWarp, smem, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 
-#define CM3_CK_GEOMS(X) \
-    X(3, 8, 2)          \
-    X(3, 16, 2)         \
-    X(3, 2, 2)          \
-    X(3, 4, 2)          \
-    X(5, 8, 2)          \
-    X(3, 8, 1)          \
-    X(3, 8, 3)
+// boards with the geometry compiled in: the reference's configs (alg/config_checkers_stage{1,2}.json:
+// 3 x 8, n_obs 2) and the constructor's default board (env/checkers.py:5: 3 x 16, n_obs 2)
+#define CM3_CK_STATIC_GEOMS(X) \
+    X(3, 8, 2)                 \
+    X(3, 16, 2)
 
 template <typename Real, typename Tile>
 static int dispatch_ck(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
-#define X(r, c, o)                                                      \
-    if (R == r && C == c && O == o) {                                   \
-        switch (N) {                                                    \
-            case 1: return launch_ck<r, c, o, 1, Real, Tile>(p, stream);      \
-            case 2: return launch_ck<r, c, o, 2, Real, Tile>(p, stream);      \
-            case 3: return launch_ck<r, c, o, 3, Real, Tile>(p, stream);      \
-            case 4: return launch_ck<r, c, o, 4, Real, Tile>(p, stream);      \
-            default: break;                                             \
-        }                                                               \
+    if (N <= 4 && !dyn_geometry_forced()) {
+#define X(r, c, o)                                                                             \
+    if (R == r && C == c && O == o) {                                                          \
+        using Geo = StaticGeo<r, c, o>;                                                        \
+        const Geo g{};                                                                         \
+        switch (N) {                                                                           \
+            case 1: return launch_ck<Geo, 1, Real, Tile>(g, p, stream);                        \
+            case 2: return launch_ck<Geo, 2, Real, Tile>(g, p, stream);                        \
+            case 3: return launch_ck<Geo, 3, Real, Tile>(g, p, stream);                        \
+            case 4: return launch_ck<Geo, 4, Real, Tile>(g, p, stream);                        \
+            default: break;                                                                    \
+        }                                                                                      \
     }
-    CM3_CK_GEOMS(X)
+        CM3_CK_STATIC_GEOMS(X)
 #undef X
-    set_error("no compiled Checkers kernel for n_rows=%d n_columns=%d n_obs=%d n_agents=%d", R, C, O, N);
+    }
+    const DynGeo g(R, C, O);
+    switch (N) {
+        case 1: return launch_ck<DynGeo, 1, Real, Tile>(g, p, stream);
+        case 2: return launch_ck<DynGeo, 2, Real, Tile>(g, p, stream);
+        case 3: return launch_ck<DynGeo, 3, Real, Tile>(g, p, stream);
+        case 4: return launch_ck<DynGeo, 4, Real, Tile>(g, p, stream);
+        case 5: return launch_ck<DynGeo, 5, Real, Tile>(g, p, stream);
+        case 6: return launch_ck<DynGeo, 6, Real, Tile>(g, p, stream);
+        case 7: return launch_ck<DynGeo, 7, Real, Tile>(g, p, stream);
+        case 8: return launch_ck<DynGeo, 8, Real, Tile>(g, p, stream);
+        default: break;
+    }
+    set_error("n_agents=%d outside 1..%d", N, CM3_MAX_AGENTS);
     return CM3_ERR_UNSUPPORTED;
 }
 
 // This file is compiled three times (cm3_b200/build.py): -DCM3_CK_REAL=0 instantiates the float
 // kernels, =1 the double ones, =2 the float kernels with int8 tiles; the objects build in parallel.
 #if CM3_CK_REAL == 0
+// what the bitboards and the packed words can address (the header states the same limits)
 bool checkers_geometry_supported(int R, int C, int O, int N) {
-    if (N < 1 || N > CM3_MAX_AGENTS) return false;
-#define X(r, c, o) \
-    if (R == r && C == c && O == o) return true;
-    CM3_CK_GEOMS(X)
-#undef X
-    return false;
+    return N >= 1 && N <= CM3_MAX_AGENTS && R >= 1 && C >= 2 && O >= 1 && O <= 3 && R * C <= 64 &&
+           C + 2 * O + 1 <= 32 && R + 2 * O <= kCkMaxTR && C + 2 * O + 1 <= kCkMaxTC && R * C / 2 + 1 <= kCkMaxCnt;
 }
+
+int checkers_tile_envs(int N) { return kWarp / ck_lanes_per_env(N); }
 
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
     return dispatch_ck<float, float>(R, C, O, N, p, stream);

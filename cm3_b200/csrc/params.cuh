@@ -19,17 +19,20 @@ enum PtMode { kPtStep = 0, kPtReset = 1 };
 
 struct CkOut {
     char *grid, *vec, *obs_others, *obs_self_t, *obs_self_v, *reward, *local_rewards;
-    uint8_t *done;
+    uint8_t *done, *goal_idx;
 };
 struct PtOut {
     char *global_state, *obs_others, *obs_self, *reward, *reward_n;
     uint8_t *done;
+    int32_t *collisions;
+    uint8_t *reached;
 };
 
 struct CkParams {
     uint64_t *remaining;
     uint32_t *agents;
     uint32_t *meta;
+    uint32_t *sync;  // per-tile launch-chaining words (common.cuh: TileTicket), may be NULL
     const int8_t *actions;
     const uint8_t *goal_idx;
     const uint8_t *env_mask;
@@ -41,6 +44,10 @@ struct CkParams {
     int n_dst;
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
+    int chained;      // 1: wait for this tile's predecessor only (TileTicket) instead of griddepcontrol.wait
+    int random_goal;  // N == 1: in-kernel resets redraw the goal (train_offpolicy.py:291-296)
+    int R, C, O;      // board geometry for the kernels that take it as data (checkers.cu: DynGeo)
+    unsigned long long color_mask[2];  // bitboard of the green / orange cells (checkers.py:54-63)
     unsigned long long seed;
     long long t0, env_id_offset;
     int start_r[CM3_MAX_AGENTS], start_c[CM3_MAX_AGENTS];  // expanded coordinates
@@ -63,6 +70,7 @@ struct PtParams {
     char *sv, *landmarks;
     int32_t *steps, *collisions;
     uint8_t *reached;
+    uint32_t *sync;  // see CkParams
     const int8_t *actions;
     int8_t *actions_out;
     const char *init_pos, *init_landmarks;
@@ -71,9 +79,11 @@ struct PtParams {
     int n_dst;
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
+    int chained;  // see CkParams
     unsigned long long seed;
     long long t0, env_id_offset, reset_counter;
     double dt, damping, contact_force, contact_margin, dist_min, mass, sensitivity, reach_thresh;
+    double dist_min2;  // dist_min * dist_min (particle.cu: Contact<float>)
     double agents_x[CM3_MAX_AGENTS], agents_y[CM3_MAX_AGENTS];
     double landmarks_x[CM3_MAX_AGENTS], landmarks_y[CM3_MAX_AGENTS];
     double initial_std, prob_random;
@@ -84,6 +94,8 @@ struct PtParams {
 };
 
 bool checkers_geometry_supported(int R, int C, int O, int N);
+int checkers_tile_envs(int N);  // envs per warp tile of the Checkers kernels
+bool dyn_geometry_forced();    // CM3_CK_DYNAMIC=1: always take the geometry-as-data kernels (tests)
 int checkers_launch(int R, int C, int O, int N, int real, int tile, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);

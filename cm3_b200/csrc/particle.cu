@@ -45,20 +45,20 @@ namespace cm3 {
 
 template <typename Real> __device__ __forceinline__ void ld4(const Real *p, Real &a, Real &b, Real &c, Real &d);
 template <> __device__ __forceinline__ void ld4<float>(const float *p, float &a, float &b, float &c, float &d) {
-    const float4 v = *reinterpret_cast<const float4 *>(p);
+    const float4 v = __ldcg(reinterpret_cast<const float4 *>(p));  // state: L2 (launch chaining reads it under an acquire)
     a = v.x; b = v.y; c = v.z; d = v.w;
 }
 template <> __device__ __forceinline__ void ld4<double>(const double *p, double &a, double &b, double &c, double &d) {
-    const double2 u = reinterpret_cast<const double2 *>(p)[0], v = reinterpret_cast<const double2 *>(p)[1];
+    const double2 u = __ldcg(reinterpret_cast<const double2 *>(p)), v = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
     a = u.x; b = u.y; c = v.x; d = v.y;
 }
 template <typename Real> __device__ __forceinline__ void ld2(const Real *p, Real &a, Real &b);
 template <> __device__ __forceinline__ void ld2<float>(const float *p, float &a, float &b) {
-    const float2 v = *reinterpret_cast<const float2 *>(p);
+    const float2 v = __ldcg(reinterpret_cast<const float2 *>(p));
     a = v.x; b = v.y;
 }
 template <> __device__ __forceinline__ void ld2<double>(const double *p, double &a, double &b) {
-    const double2 v = *reinterpret_cast<const double2 *>(p);
+    const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
     a = v.x; b = v.y;
 }
 template <typename Real> __device__ __forceinline__ const PtConsts<Real> &pt_consts(const PtParams &p);
@@ -85,24 +85,33 @@ template <typename Real> __device__ __forceinline__ Real logaddexp0(Real x) {
 
 // Contact geometry of one agent pair (core.py:186-192): delta, dist and the softplus argument
 // x = -(dist - dist_min)/k.  k = 1e-3 makes x ill-conditioned - an ulp of dist is 1000 ulps of x -
-// so the float kernel evaluates exactly this sub-expression in double from the (exact) float
-// positions; everything else stays in Real.
+// so the float kernel cannot evaluate it in float.  Round 1 evaluated the literal expression in
+// double (DSQRT + DDIV: two ~100-cycle dependent sequences on every in-contact pair, which is
+// every step of the merge scenario).  The cancellation is all in (dist - dist_min); written as
+//     dist - dist_min = (dist^2 - dist_min^2) / (dist + dist_min)
+// it sits in the NUMERATOR, which is exact-ish in double from the exact float positions with five
+// short double operations (sub, sub, mul, fma, sub), while the denominator (dist + dist_min) * k has
+// no cancellation and is evaluated in float: x agrees with the double evaluation to ~2 float ulps
+// (tests/test_gpu_particle.py compares against the float64 oracle at rtol 1e-5).
 template <typename Real> struct Contact;
 template <> struct Contact<float> {
-    static __device__ __forceinline__ void eval(float px, float py, float qx, float qy, double dist_min, double k,
+    static __device__ __forceinline__ void eval(float px, float py, float qx, float qy, const PtParams &p,
                                                 float &dx, float &dy, float &dist, float &x) {
         const double ddx = __dsub_rn((double)px, (double)qx), ddy = __dsub_rn((double)py, (double)qy);
-        const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-        dx = (float)ddx; dy = (float)ddy; dist = (float)d;
-        x = (float)(-__ddiv_rn(__dsub_rn(d, dist_min), k));
+        const double q = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));   // dist^2, exact to a double ulp
+        const float num = (float)__dsub_rn(q, p.dist_min2);
+        dx = (float)ddx; dy = (float)ddy;
+        dist = __fsqrt_rn((float)q);
+        const float den = __fmul_rn(__fadd_rn(dist, p.kf.dist_min), p.kf.contact_margin);
+        x = -__fdiv_rn(num, den);
     }
 };
 template <> struct Contact<double> {
-    static __device__ __forceinline__ void eval(double px, double py, double qx, double qy, double dist_min, double k,
+    static __device__ __forceinline__ void eval(double px, double py, double qx, double qy, const PtParams &p,
                                                 double &dx, double &dy, double &dist, double &x) {
         dx = __dsub_rn(px, qx); dy = __dsub_rn(py, qy);
         dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-        x = -__ddiv_rn(__dsub_rn(dist, dist_min), k);
+        x = -__ddiv_rn(__dsub_rn(dist, p.dist_min), p.contact_margin);
     }
 };
 
@@ -118,11 +127,11 @@ template <typename Real> struct ResetDraw { Real px, py, lx, ly; };
 
 template <typename Real>
 __device__ __noinline__ ResetDraw<Real> draw_reset(const PtParams &p, unsigned long long genv,
-                                                   unsigned long long counter, int a) {
+                                                   unsigned long long counter, uint32_t tag, int a) {
     using Op = RealOps<Real>;
     ResetDraw<Real> d;
     const uint32_t c0 = (uint32_t)genv, c1 = (uint32_t)(genv >> 32);
-    const uint32_t c2 = (uint32_t)counter, c3 = kTagReset | ((uint32_t)(counter >> 32) & 0xFFFFu);
+    const uint32_t c2 = (uint32_t)counter, c3 = tag | ((uint32_t)(counter >> 32) & 0xFFFFu);
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
     bool randomise = false;
     if (p.prob_random > 0.0) {  // rand_num, :75
@@ -151,18 +160,24 @@ __device__ __noinline__ ResetDraw<Real> draw_reset(const PtParams &p, unsigned l
     return d;
 }
 
-// get_collision_force for one pair in (or near) contact, core.py:180-196: the literal evaluation.
-// Out of line for the same reason as draw_reset: it is the rare path.
+// get_collision_force for one pair in (or near) contact, core.py:180-196.  Out of line where
+// contacts are the rare path (N >= 3: for the same reason as draw_reset), inline for N <= 2, where
+// the merge scenario takes it on nine steps out of ten.
 template <typename Real> struct Force2 { Real x, y; };
 
 template <typename Real>
-__device__ __noinline__ Force2<Real> contact_force(Real ax, Real ay, Real bx, Real by, double dist_min, double k,
-                                                   Real cf, Real km) {
+__device__ __forceinline__ Force2<Real> contact_force_inl(Real ax, Real ay, Real bx, Real by, const PtParams &p) {
     using Op = RealOps<Real>;
+    const PtConsts<Real> &K = pt_consts<Real>(p);
     Real dx, dy, dist, x;
-    Contact<Real>::eval(ax, ay, bx, by, dist_min, k, dx, dy, dist, x);
-    const Real pen = Op::mul(logaddexp0<Real>(x), km);
-    return Force2<Real>{Op::mul(Op::div(Op::mul(cf, dx), dist), pen), Op::mul(Op::div(Op::mul(cf, dy), dist), pen)};
+    Contact<Real>::eval(ax, ay, bx, by, p, dx, dy, dist, x);
+    const Real pen = Op::mul(logaddexp0<Real>(x), K.contact_margin);
+    return Force2<Real>{Op::mul(Op::div(Op::mul(K.contact_force, dx), dist), pen),
+                        Op::mul(Op::div(Op::mul(K.contact_force, dy), dist), pen)};
+}
+template <typename Real>
+__device__ __noinline__ Force2<Real> contact_force_ool(Real ax, Real ay, Real bx, Real by, const PtParams &p) {
+    return contact_force_inl<Real>(ax, ay, bx, by, p);
 }
 
 // 16-byte chunks per env record S = odd * 2^k: lanes one record apart collide on the 8 bank groups
@@ -199,7 +214,9 @@ struct PtGeom {
     static constexpr int kStages = (N <= 2 && 14 * (2 * kSetBytes + kOverhead + 1024 /* driver-reserved */) <= 227 * 1024) ? 2 : 1;
     static constexpr int kActOff = kStages * kSetBytes;             // ActionStream slots
     static constexpr int kSmemBytes = kActOff + kOverhead;
-    static_assert(kRowRows <= 256 && kOthRows <= 256, "TMA box dimension");
+    // a TMA box has at most 256 rows: the wide records of N >= 6 (and N = 5..8 in double) do not fit
+    // one box per tile and take the linear tile + plain bulk stores instead
+    static constexpr bool kTmaOk = kRowRows <= 256 && kOthRows <= 256;
 };
 
 // Stores 4 Reals at byte offset `off` of a staging tile laid out in the TMA swizzle pattern
@@ -239,12 +256,15 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
     constexpr int NO = Gm::NO, LO = Gm::LO;
     constexpr uint32_t RS = (uint32_t)sizeof(Real);
 
-    pdl_launch_dependents();  // the next step's grid may become resident while this one drains
+    const int lane = threadIdx.x;
+    // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
+    TileTicket ticket;
+    ticket.take(p.sync, blockIdx.x, lane);
+    if (ticket.mine != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *stage_base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
-    const int lane = threadIdx.x;
     const bool reset_mode = !FULL && p.mode == kPtReset;
     const int env0 = blockIdx.x * kWarp;
     const int env = env0 + lane;
@@ -277,10 +297,15 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
     Real *rn_ptr = reinterpret_cast<Real *>(o0.reward_n) + (oe0 + env) * N;
     Real *rw_ptr = reinterpret_cast<Real *>(o0.reward) + (oe0 + env);
     uint8_t *dn_ptr = o0.done + (oe0 + env);
+    const bool has_cl = o0.collisions != nullptr;  // optional in every instantiation
+    int32_t *cl_ptr = o0.collisions + (oe0 + env);
+    const bool has_rc = o0.reached != nullptr;
+    uint8_t *rc_ptr = o0.reached + (oe0 + env);
     int tile_idx = (int)((oe0 + env0) / kWarp);  // tensor-map tile coordinate (tma: out_B, out_env0 % 32 == 0)
     const int tiles_per_slot = (int)(OB / kWarp);
 
-    pdl_wait();  // state written by the previous launch is visible from here on
+    // the state this tile's previous launch wrote is visible from here on
+    if (p.chained) ticket.wait(lane); else pdl_wait();
 
     // ---- state of my env: all agents in registers
     Real vx[N], vy[N], px[N], py[N], lx[N], ly[N];
@@ -294,20 +319,20 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
             ld4<Real>(reinterpret_cast<const Real *>(p.sv) + ((size_t)env * N + i) * 4, vx[i], vy[i], px[i], py[i]);
             ld2<Real>(reinterpret_cast<const Real *>(p.landmarks) + ((size_t)env * N + i) * 2, lx[i], ly[i]);
         }
-        steps = p.steps[env];
-        collisions = p.collisions[env];
-        reached = p.reached[env];
+        steps = __ldcg(p.steps + env);
+        collisions = __ldcg(p.collisions + env);
+        reached = __ldcg(p.reached + env);
     }
 
     // multi-goal_spread.py:65-93 on Philox (or the injected host draws)
-    auto reset_state = [&](unsigned long long counter) {
+    auto reset_state = [&](unsigned long long counter, uint32_t tag) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (reset_mode && p.init_pos != nullptr) {
                 ld2<Real>(reinterpret_cast<const Real *>(p.init_pos) + ((size_t)env * N + i) * 2, px[i], py[i]);
                 ld2<Real>(reinterpret_cast<const Real *>(p.init_landmarks) + ((size_t)env * N + i) * 2, lx[i], ly[i]);
             } else {
-                const ResetDraw<Real> d = draw_reset<Real>(p, (unsigned long long)(p.env_id_offset + env), counter, i);
+                const ResetDraw<Real> d = draw_reset<Real>(p, (unsigned long long)(p.env_id_offset + env), counter, tag, i);
                 px[i] = d.px; py[i] = d.py; lx[i] = d.lx; ly[i] = d.ly;
             }
             vx[i] = 0; vy[i] = 0;
@@ -412,19 +437,28 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
         bool sel = false;
         if (reset_mode) {
             sel = valid && (p.env_mask == nullptr || p.env_mask[env] != 0);
-            if (sel) reset_state((unsigned long long)p.reset_counter);
+            if (sel) reset_state((unsigned long long)p.reset_counter, kTagReset);
         } else {
             // ---- actions -> control forces (environment.py:194-214, core.py:134-140)
             int act[N];
             if (p.actions != nullptr) {
-                uint32_t w = act_word;  // picked up from the stream during the previous emit
-                if (!acts.on && valid) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
+                if constexpr (N <= 4) {
+                    uint32_t w = act_word;  // picked up from the stream during the previous emit
+                    if (!acts.on && valid) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
 #pragma unroll
-                for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
+                    for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) act[i] = valid ? (int)p.actions[((size_t)t * B + env) * N + i] : 0;
+                }
             } else {
-                const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env), (uint64_t)(p.t0 + t));
+                // one Philox block of 4 words per 4 agents
 #pragma unroll
-                for (int i = 0; i < N; ++i) act[i] = action_from_word(philox_word(w, i), 5);
+                for (int i0 = 0; i0 < N; i0 += 4) {
+                    const Philox4 w = philox_action_words(p.seed, (uint64_t)(p.env_id_offset + env), (uint64_t)(p.t0 + t), i0 / 4);
+#pragma unroll
+                    for (int i = i0; i < N && i < i0 + 4; ++i) act[i] = action_from_word(philox_word(w, i - i0), 5);
+                }
             }
             if (p.actions_out != nullptr && valid) {
 #pragma unroll
@@ -469,8 +503,9 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
 #pragma unroll
                         for (int b = a + 1; b < N; ++b) {
                             if (!(d2c[q] > far2)) {  // the literal evaluation
-                                const Force2<Real> F = contact_force<Real>(px[a], py[a], px[b], py[b], p.dist_min,
-                                                                           p.contact_margin, cf, km);
+                                Force2<Real> F;
+                                if constexpr (N <= 2) F = contact_force_inl<Real>(px[a], py[a], px[b], py[b], p);
+                                else F = contact_force_ool<Real>(px[a], py[a], px[b], py[b], p);
                                 fx[a] = Op::add(F.x, fx[a]); fy[a] = Op::add(F.y, fy[a]);    // f_a + p_force[a]
                                 fx[b] = Op::add(-F.x, fx[b]); fy[b] = Op::add(-F.y, fy[b]);  // f_b = -force
                             }
@@ -542,14 +577,19 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
                     // destination d: same cursors, rebased from set 0 to set d (GATHER only)
                     Real *rn = rn_ptr, *rw = rw_ptr;
                     uint8_t *dn = dn_ptr;
+                    int32_t *cl = cl_ptr;
+                    uint8_t *rc = rc_ptr;
                     if (GATHER && d > 0) {
+                        rc = p.out[d].reached + (rc_ptr - o0.reached);
                         rn = reinterpret_cast<Real *>(p.out[d].reward_n + (reinterpret_cast<char *>(rn_ptr) - o0.reward_n));
                         rw = reinterpret_cast<Real *>(p.out[d].reward + (reinterpret_cast<char *>(rw_ptr) - o0.reward));
                         dn = p.out[d].done + (dn_ptr - o0.done);
+                        cl = p.out[d].collisions + (cl_ptr - o0.collisions);
                     }
                     if (has_rn) {
-                        if (N == 4) {
-                            st4<Real>(rn, rew[0], rew[N > 1 ? 1 : 0], rew[N > 2 ? 2 : 0], rew[N > 3 ? 3 : 0]);
+                        if (N % 4 == 0) {
+#pragma unroll
+                            for (int i = 0; i + 3 < N; i += 4) st4<Real>(rn + i, rew[i], rew[i + 1 < N ? i + 1 : 0], rew[i + 2 < N ? i + 2 : 0], rew[i + 3 < N ? i + 3 : 0]);
                         } else {
 #pragma unroll
                             for (int i = 0; i < N; ++i) rn[i] = rew[i];
@@ -557,10 +597,12 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
                     }
                     if (has_rw) *rw = total;
                     if (has_dn) *dn = done ? 1 : 0;
+                    if (has_cl) *cl = collisions;  // the episode's count so far, before a reset zeroes it
+                    if (has_rc) *rc = (uint8_t)reach_bits;
                 }
             }
-            rn_ptr += OB * N; rw_ptr += OB; dn_ptr += OB;
-            if (p.auto_reset && done) reset_state((unsigned long long)(p.t0 + t + 1));
+            rn_ptr += OB * N; rw_ptr += OB; dn_ptr += OB; cl_ptr += OB; rc_ptr += OB;
+            if (p.auto_reset && done) reset_state((unsigned long long)(p.t0 + t + 1), kTagAutoReset);
         }
         emit(t);
         if (sel && o0.done != nullptr) o0.done[oe0 + env] = 0;  // np.any(done_n), environment.py:149
@@ -579,6 +621,7 @@ __global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constan
         p.collisions[env] = collisions;
         p.reached[env] = (uint8_t)reached;
     }
+    ticket.publish(lane);  // this tile's next launch may go ahead
     // shared memory must outlive the async reads; the global writes themselves complete with the grid
     if (pending && lane == 0) bulk_wait_read();
 }
@@ -616,13 +659,8 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
     using Gm = PtGeom<N, Real>;
     auto kern = particle_kernel<N, Real, GATHER, FULL>;
     constexpr int kSmem = Gm::kSmemBytes;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    CM3_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !attr_set[dev]) {
-        CM3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_set[dev] = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    CM3_CUDA(ensure_smem_attr(kern, kSmem, attr_done));
     const int nblocks = (p.B + kWarp - 1) / kWarp;
     CM3_CUDA(launch_kernel(kern, nblocks, kWarp, kSmem, stream, pdl_enabled(), p));
     return CM3_OK;
@@ -633,7 +671,7 @@ template <int N, typename Real>
 static void make_tensor_maps(PtParams &p) {
     using Gm = PtGeom<N, Real>;
     p.tma = 0;
-    if (p.n_dst == 1 && tma_enabled() && p.B % kWarp == 0 && p.out_B % kWarp == 0 && p.out_env0 % kWarp == 0) {
+    if (Gm::kTmaOk && p.n_dst == 1 && tma_enabled() && p.B % kWarp == 0 && p.out_B % kWarp == 0 && p.out_env0 % kWarp == 0) {
         const int T = (p.mode == kPtReset) ? 1 : p.T;
         const size_t envs = (size_t)T * (size_t)p.out_B;
         const PtOut &o = p.out[0];
@@ -654,14 +692,17 @@ static int dispatch_pt(const PtParams &p0, cudaStream_t stream) {
     // FULL: the step / rollout launch with nothing optional left to test at run time
     const bool full = p.tma && p.mode == kPtStep && p.mass == 1.0 && o.global_state && o.obs_self && o.obs_others &&
                       o.reward && o.reward_n && o.done && full_enabled();
-    return full ? launch_pt<N, Real, false, true>(p, stream) : launch_pt<N, Real, false, false>(p, stream);
+    if constexpr (PtGeom<N, Real>::kTmaOk) {
+        if (full) return launch_pt<N, Real, false, true>(p, stream);
+    }
+    return launch_pt<N, Real, false, false>(p, stream);
 }
 
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream) {
 #define CASE(n) \
     case n: return real == CM3_REAL_F64 ? dispatch_pt<n, double>(p, stream) : dispatch_pt<n, float>(p, stream);
     switch (N) {
-        CASE(1) CASE(2) CASE(3) CASE(4)
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
         default: break;
     }
 #undef CASE

@@ -29,8 +29,12 @@ class Checkers(object):
                                 dtype=torch.float64)
 
     # ------------------------------------------------------------------ tuple assembly
-    def _host(self, out, fields):
-        return {f: out[f].cpu().numpy()[0] for f in fields}
+    _OBS = ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v")
+
+    def _host(self, views, fields):
+        # `views` are windows of the pinned host mirror (one device-to-host copy per call of the
+        # facade); the reference hands out fresh arrays, so each field is copied out
+        return {f: views[f][0].copy() for f in fields}
 
     def _obs_tuple(self, o):
         n = self.n_agents
@@ -47,24 +51,23 @@ class Checkers(object):
         if self.n_agents == 1:  # :271-276 - the start row follows the goal
             goal_idx = np.where(g[0] == 1)[0][0]
             self.agents_r = np.array([0 if goal_idx == 0 else 2]) + self.n_obs
-        out = self._vec.reset(goals=g.reshape(self.n_agents, 2))
-        o = self._host(out, ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v"))
+        self._vec.reset(goals=g.reshape(self.n_agents, 2))
+        o = self._host(self._vec.download(), self._OBS)
         return self._obs_tuple(o) + (False,)
 
     def step(self, actions):
         """Returns (global_state, obs_others, obs_self_t, obs_self_v, total_reward, local_rewards,
         done), checkers.py:262."""
         a = np.asarray(actions).reshape(1, self.n_agents)
-        out = self._vec.step(a)
-        o = self._host(out, ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "reward",
-                             "local_rewards", "done"))
+        # host actions in, every field out in one packed copy (cm3_checkers_step_host_packed)
+        o = self._host(self._vec.step_host(a), self._OBS + ("reward", "local_rewards", "done"))
         local_rewards = [float(x) for x in o["local_rewards"]]
         return self._obs_tuple(o) + (np.float64(o["reward"]), local_rewards, bool(o["done"]))
 
     # ------------------------------------------------------------------ read-only views of state
     def _observe(self):
-        out = self._vec.reset(mask=np.zeros(1, dtype=np.uint8))  # no env selected: observe only
-        return self._host(out, ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v"))
+        self._vec.reset(mask=np.zeros(1, dtype=np.uint8))  # no env selected: observe only
+        return self._host(self._vec.download(), self._OBS)
 
     def get_valid_grid(self):
         return self._observe()["grid"]

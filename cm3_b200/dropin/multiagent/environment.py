@@ -68,7 +68,7 @@ class MultiAgentEnv(object):
         self._vec = VecParticle(1, self.n, scenario.config, prob_random=scenario.prob_random,
                                 max_steps=max_steps, device=device, dtype=torch.float64, **overrides)
         self._results = None
-        self._synced = None
+        self._handed_out = None
         scenario._env = self
         self._upload_world()   # make_world() already drew an initial state (multi-goal_spread.py:62)
 
@@ -77,11 +77,33 @@ class MultiAgentEnv(object):
         self._reset_render()
 
     # ------------------------------------------------------------------ host <-> device sync
+    # The entity objects (world.agents[i].state.p_pos ...) are the reference's public state; the
+    # device holds the authoritative copy.  After every launch the arrays handed to the entities are
+    # READ-ONLY views of that launch's results, and the env remembers which array objects it handed
+    # out: a caller that wants to move an entity assigns a new array (as reset_world does), which a
+    # dozen identity checks detect - no value comparison, no device read, on the per-step path.
     def _host_arrays(self):
         pos = np.array([a.state.p_pos for a in self.world.agents], dtype=np.float64)
         vel = np.array([a.state.p_vel for a in self.world.agents], dtype=np.float64)
         lm = np.array([l.state.p_pos for l in self.world.landmarks], dtype=np.float64)
         return pos, vel, lm
+
+    def _entity_arrays(self):
+        w = self.world
+        return [a.state.p_pos for a in w.agents] + [a.state.p_vel for a in w.agents] + [l.state.p_pos for l in w.landmarks]
+
+    def _remember(self):
+        self._handed_out = self._entity_arrays()
+        self._handed_flags = ([bool(a.reached) for a in self.world.agents], self.scenario.collisions, self.steps)
+
+    def _stale(self):
+        h = self._handed_out
+        if h is None:
+            return True
+        cur = self._entity_arrays()
+        if len(cur) != len(h) or any(x is not y for x, y in zip(cur, h)):
+            return True
+        return self._handed_flags != ([bool(a.reached) for a in self.world.agents], self.scenario.collisions, self.steps)
 
     def _upload_world(self):
         """Host entity objects -> device state (after reset_world or a manual edit)."""
@@ -90,46 +112,46 @@ class MultiAgentEnv(object):
         self._vec.set_state(pos=pos[None], vel=vel[None], landmarks=lm[None],
                             steps=np.array([self.steps]), collisions=np.array([self.scenario.collisions]),
                             reached=reached)
-        self._synced = (pos, vel, lm)
+        self._remember()
         self._results = None
 
     def _world_was_reset(self):
-        self._synced = None
+        self._handed_out = None
         self._results = None
 
     def _ensure_synced(self):
-        pos, vel, lm = self._host_arrays()
-        if self._synced is None or not all(np.array_equal(a, b) for a, b in zip((pos, vel, lm), self._synced)):
+        if self._stale():
             self._upload_world()
 
-    def _download(self, out, with_reward):
-        fields = ("global_state", "obs_others", "obs_self", "done") + (("reward", "reward_n") if with_reward else ())
-        res = {f: out[f].cpu().numpy()[0] for f in fields}
+    def _adopt(self, views, with_reward):
+        """Takes the results of the last launch (windows of the pinned host mirror, one device-to-host
+        copy) into the entity objects and the scenario."""
+        fields = ("global_state", "obs_others", "obs_self", "done") + (("reward", "reward_n", "collisions", "reached") if with_reward else ())
+        res = {f: views[f][0].copy() for f in fields}
         if not with_reward:
             res["reward"] = res["reward_n"] = None
         gs = res["global_state"]
+        gs.flags.writeable = False
         for i, agent in enumerate(self.world.agents):
-            agent.state.p_vel = gs[i, 0:2].copy()
-            agent.state.p_pos = gs[i, 2:4].copy()
-        reached = int(self._vec.state["reached"].cpu().numpy()[0])
-        for i, agent in enumerate(self.world.agents):
-            agent.reached = bool((reached >> i) & 1)
-        self.scenario.collisions = int(self._vec.state["collisions"].cpu().numpy()[0])
-        self._synced = self._host_arrays()
+            agent.state.p_vel = gs[i, 0:2]
+            agent.state.p_pos = gs[i, 2:4]
+        if with_reward:   # a reset / observe-only launch leaves reached and the counter as they are
+            reached = int(res["reached"])
+            for i, agent in enumerate(self.world.agents):
+                agent.reached = bool((reached >> i) & 1)
+            self.scenario.collisions = int(res["collisions"])
+        self._remember()
         self._results = res
         return res
 
     def _current_results(self):
         """Results for the scenario callbacks: the last launch's, or a fresh observe-only launch
         when the host state changed since."""
-        pos, vel, lm = self._host_arrays()
-        stale = self._results is None or self._synced is None or \
-            not all(np.array_equal(a, b) for a, b in zip((pos, vel, lm), self._synced))
-        if stale:
+        if self._results is None or self._stale():
             keep = self._results
             self._upload_world()
-            out = self._vec.reset(mask=np.zeros(1, dtype=np.uint8))  # observe only
-            res = self._download(out, with_reward=False)
+            self._vec.reset(mask=np.zeros(1, dtype=np.uint8))  # observe only
+            res = self._adopt(self._vec.download(), with_reward=False)
             if keep is not None and keep.get("reward_n") is not None:
                 res["reward"], res["reward_n"] = keep["reward"], keep["reward_n"]
         return self._results
@@ -139,12 +161,10 @@ class MultiAgentEnv(object):
         """-> (global_state [N,4], obs_others_n, obs_n, reward, reward_n, done), environment.py:123"""
         self.agents = self.world.policy_agents
         self._ensure_synced()
-        a = np.zeros((1, self.n), dtype=np.int64)
-        for i in range(self.n):
-            a[0, i] = int(action_n[i])
-        out = self._vec.step(a)
+        a = np.array([[int(x) for x in action_n[:self.n]]], dtype=np.int64)
         self.steps += 1
-        res = self._download(out, with_reward=True)
+        # host actions in, every field (and the reached / collision flags) out in one packed copy
+        res = self._adopt(self._vec.step_host(a), with_reward=True)
         obs_n, obs_others_n, reward_n, done_n = [], [], [], []
         for agent in self.agents:   # callback order of environment.py:95-104
             obs_self, obs_others = self._get_obs(agent)
@@ -163,10 +183,9 @@ class MultiAgentEnv(object):
         self.reset_callback(self.world)      # host RNG draws, like the reference
         self._reset_render()
         self.steps = 0
-        self._upload_world()
-        pos, vel, lm = self._synced
-        out = self._vec.reset(init_pos=pos[None], init_landmarks=lm[None])
-        res = self._download(out, with_reward=False)
+        pos, vel, lm = self._host_arrays()
+        self._vec.reset(init_pos=pos[None], init_landmarks=lm[None])   # zeroes velocities, steps, counters
+        res = self._adopt(self._vec.download(), with_reward=False)
         obs_n, obs_others_n, done_n = [], [], []
         self.agents = self.world.policy_agents
         for agent in self.agents:

@@ -97,13 +97,17 @@ class RolloutAllGather(object):
     mode "peer": the rollout buffers live in symmetric memory (every rank can address every
         rank's buffer over NVLink); cm3_*_rollout_gather stores each output element straight
         into all `world` buffers at this shard's env offset - compute and all-gather are ONE
-        kernel, there is no local staging buffer and no collective launch.  A barrier on the
-        stream publishes the stores.
+        kernel, there is no local staging buffer and no collective launch.
+        double_buffer=True: two symmetric buffers used in turn.  Rollout k + 1 only needs "every
+        rank is done with buffer (k + 1) & 1" - the contents of rollout k - 1 - so it is enqueued
+        right behind rollout k on the compute stream, while the barrier that publishes rollout k
+        ("all ranks' stores have landed") runs on a second stream; the consumer's stream waits for
+        that event.  With one buffer the two barriers and the kernel are strictly serial.
     mode "nccl": local rollout, then ncclAllGather per field (+ a permuting copy to time-major).
     mode "auto": "peer" when symmetric memory can be set up for the group, else "nccl".
     """
 
-    def __init__(self, env, T, shard=None, group=None, mode="auto", fields=None):
+    def __init__(self, env, T, shard=None, group=None, mode="auto", fields=None, double_buffer=False):
         self.env, self.T = env, int(T)
         self.shard = shard or EnvShard(env.B if not dist.is_initialized() else env.B * dist.get_world_size())
         if self.shard.count != env.B:
@@ -113,7 +117,9 @@ class RolloutAllGather(object):
         self.group = group
         self.fields = tuple(fields) if fields is not None else tuple(env.field_shapes().keys())
         self.mode = mode
+        self.nbuf = 2 if double_buffer else 1
         self._hdl = None
+        self._k = 0
         if mode in ("auto", "peer"):
             try:
                 self._setup_peer()
@@ -123,7 +129,7 @@ class RolloutAllGather(object):
                     raise
                 self.mode, self.peer_error = "nccl", repr(e)
         if self.mode == "nccl":
-            self.local = {k: v for k, v in env.alloc_outputs(self.T).items() if k in self.fields}
+            self.local = {k: v for k, v in env.alloc_outputs(self.T, fields=self.fields).items()}
 
     # ------------------------------------------------------------------ peer mode
     def _field_layout(self):
@@ -146,26 +152,61 @@ class RolloutAllGather(object):
             raise ValueError("peer mode addresses at most 8 GPUs (one NVSwitch node)")
         layout, total = self._field_layout()
         dev = self.env.device
-        buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
         grp = self.group if self.group is not None else dist.group.WORLD
-        hdl = symm_mem.rendezvous(buf, grp)
-        self._buf, self._hdl, self._layout = buf, hdl, layout
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        self.gathered = {k: buf[off:off + int(torch.Size(shp).numel()) * dt.itemsize].view(dt).view(shp)
-                         for k, (off, shp, dt) in layout.items()}
-        self._dst_ptrs = [{k: ptrs[r] + layout[k][0] for k in self.fields} for r in range(self.shard.world)]
+        self._bufs, self._hdls, self._gathered, self._dsts = [], [], [], []
+        for i in range(self.nbuf):
+            buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(buf, grp)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self._bufs.append(buf)
+            self._hdls.append(hdl)
+            self._gathered.append({k: buf[off:off + int(torch.Size(shp).numel()) * dt.itemsize].view(dt).view(shp)
+                                   for k, (off, shp, dt) in layout.items()})
+            self._dsts.append([{k: ptrs[r] + layout[k][0] for k in self.fields} for r in range(self.shard.world)])
+        self._layout = layout
+        self._hdl, self.gathered, self._dst_ptrs = self._hdls[0], self._gathered[0], self._dsts[0]
+        if self.nbuf == 2:
+            self._pub_stream = torch.cuda.Stream(device=dev)
+            self._stepped = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     # ------------------------------------------------------------------ API
-    def rollout(self, actions=None, seed=0, t0=0, auto_reset=False, time_major=True):
+    def rollout(self, actions=None, seed=0, t0=0, auto_reset=False, time_major=True, wait=True):
+        """Returns the gathered field dict of this rollout.  peer mode with double_buffer: the
+        buffers alternate, and with wait=False the caller's stream is NOT made to wait for the
+        publishing barrier - call wait_ready(result) (or rollout(..., wait=True)) before reading."""
         env = self.env
         if self.mode == "peer":
-            self._hdl.barrier()  # every rank is done reading the previous contents
-            env.rollout_gather(self.T, self._dst_ptrs, self.shard.total_envs, self.shard.start,
+            i = self._k % self.nbuf
+            self._k += 1
+            hdl = self._hdls[i]
+            hdl.barrier(channel=0)  # every rank is done reading the previous contents of buffer i
+            env.rollout_gather(self.T, self._dsts[i], self.shard.total_envs, self.shard.start,
                                actions=actions, seed=seed, t0=t0, auto_reset=auto_reset)
-            self._hdl.barrier()  # all ranks' stores have landed
-            return self.gathered
+            if self.nbuf == 1:
+                hdl.barrier(channel=0)  # all ranks' stores have landed
+                return self._gathered[0]
+            cur = torch.cuda.current_stream(env.device)
+            self._stepped[i].record(cur)
+            with torch.cuda.stream(self._pub_stream):
+                self._pub_stream.wait_event(self._stepped[i])
+                hdl.barrier(channel=1)  # all ranks' stores into buffer i have landed
+                self._ready[i].record(self._pub_stream)
+            if wait and self._k >= 2:
+                # steady state of a pipelined consumer: it reads rollout k - 1 while rollout k is in flight
+                cur.wait_event(self._ready[(i + 1) % 2])
+            self._last = i
+            return self._gathered[i]
         env.rollout(self.T, actions=actions, seed=seed, t0=t0, auto_reset=auto_reset, out=self.local)
         return all_gather_rollout(self.local, self.shard, self.group, time_major=time_major)
+
+    def wait_ready(self, gathered=None):
+        """Makes the current stream wait until the given (default: the latest) rollout's data from
+        every rank has landed in this GPU's buffer."""
+        if self.mode != "peer" or self.nbuf == 1:
+            return
+        i = self._last if gathered is None else next(j for j, g in enumerate(self._gathered) if g is gathered)
+        torch.cuda.current_stream(self.env.device).wait_event(self._ready[i])
 
     def bytes_moved_per_rollout(self):
         """Bytes this rank sends to peers (peer mode: stores over NVLink; nccl: all-gather send)."""

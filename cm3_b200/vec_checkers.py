@@ -8,10 +8,12 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from ._buffers import alloc_fields, _to_int8_host
+from ._buffers import HostRolloutBuffers, alloc_fields, _to_int8_host
 
 FIELDS = L.CheckersOutputs.FIELDS
 OBS_FIELDS = ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v")
+# the fields of the reference's return tuple (env/checkers.py:262); goal_idx is this library's extra
+REF_FIELDS = ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "reward", "local_rewards", "done")
 
 
 def _ptr(t):
@@ -24,7 +26,7 @@ class VecCheckers(object):
 
     def __init__(self, num_envs, n_rows=3, n_columns=16, n_obs=2, agents_r=(0, 2),
                  agents_c=(16, 16), n_agents=1, max_steps=50, device="cuda:0",
-                 dtype=torch.float32, env_id_offset=0, tile_dtype=None):
+                 dtype=torch.float32, env_id_offset=0, tile_dtype=None, random_goal=False):
         # the reference's own asserts (checkers.py:16-17)
         assert n_rows % 2 == 1
         assert n_columns % 2 == 0
@@ -65,17 +67,26 @@ class VecCheckers(object):
         cfg.device = dev_index
         cfg.env_id_offset = int(env_id_offset)
         self.env_id_offset = int(env_id_offset)
+        # stage 1 draws a fresh goal before every episode (train_offpolicy.py:291-296): with
+        # random_goal the in-kernel episode reset does the same from Philox
+        self.random_goal = bool(random_goal)
+        cfg.random_goal = 1 if self.random_goal else 0
         h = C.c_void_p()
         L.check(self.lib.cm3_checkers_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        tiles = C.c_int32(0)
+        L.check(self.lib.cm3_checkers_tiles(h, C.byref(tiles)))
 
         dev = self.device
         self.state = dict(
             remaining=torch.zeros(self.B, dtype=torch.int64, device=dev),
             agents=torch.zeros(self.B, self.N, dtype=torch.int32, device=dev),
             meta=torch.zeros(self.B, dtype=torch.int32, device=dev))
+        # per-tile launch-chaining words (include/cm3env.h: cm3_checkers_state.sync); not part of
+        # the env state proper: never saved, never restored
+        self._sync = torch.zeros(2, tiles.value, dtype=torch.int32, device=dev)
         self._st = L.CheckersState(_ptr(self.state["remaining"]), _ptr(self.state["agents"]),
-                                   _ptr(self.state["meta"]))
+                                   _ptr(self.state["meta"]), _ptr(self._sync))
         self.out = self.alloc_outputs()
         self._out_c = self._outputs_struct(self.out)
         self._actions_dev = torch.zeros(self.B, self.N, dtype=torch.int8, device=dev)
@@ -87,29 +98,31 @@ class VecCheckers(object):
         B, N, W = self.B, self.N, self.W
         return dict(grid=(B, self.n_rows, self.n_columns + 1, 2), vec=(B, N, 4),
                     obs_others=(B, N, self.L_others), obs_self_t=(B, N, W, W, 3),
-                    obs_self_v=(B, N, 4), reward=(B,), local_rewards=(B, N), done=(B,))
+                    obs_self_v=(B, N, 4), reward=(B,), local_rewards=(B, N), done=(B,), goal_idx=(B, N))
 
-    def bytes_per_env_step(self):
+    def bytes_per_env_step(self, fields=None):
         """Algorithmic bytes of one env-step: outputs + state read/write + actions."""
-        out = sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
         state = 2 * (8 + 4 * self.N + 4)
-        return out + state + self.N
+        return self.out_bytes_per_env_step(fields) + state + self.N
 
     def field_dtype(self, k):
-        if k == "done":
+        if k in ("done", "goal_idx"):
             return torch.uint8
         return self.tile_dtype if k in ("grid", "obs_self_t") else self.dtype
 
-    def out_bytes_per_env_step(self):
-        return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
+    def out_bytes_per_env_step(self, fields=None):
+        """Output bytes per env-step of the reference's return tuple (REF_FIELDS) or of `fields`."""
+        fields = REF_FIELDS if fields is None else fields
+        return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items() if k in fields)
 
-    def alloc_outputs(self, T=None, pinned_host=False):
-        """Zeroed output buffers: [B, ...] per field (T=None) or [T, B, ...] rollout buffers.  The
-        single-step set of a batch that is a multiple of 32 envs is one packed allocation (every
-        field stays 16-byte aligned), so that step_host needs a single device-to-host copy."""
+    def alloc_outputs(self, T=None, pinned_host=False, fields=None):
+        """Zeroed output buffers: [B, ...] per field (T=None) or [T, B, ...] rollout buffers, for
+        every field or for `fields`.  The single-step set is one packed allocation (every field
+        16-byte aligned), so that step_host needs a single device-to-host copy."""
         lead = () if T is None else (int(T),)
-        return alloc_fields(self.field_shapes(), self.field_dtype, lead, device=self.device,
-                            pinned=pinned_host, packed=T is None and self.B % 32 == 0)
+        shapes = {k: v for k, v in self.field_shapes().items() if fields is None or k in fields}
+        return alloc_fields(shapes, self.field_dtype, lead, device=self.device,
+                            pinned=pinned_host, packed=T is None)
 
     @staticmethod
     def _outputs_struct(out):
@@ -138,8 +151,14 @@ class VecCheckers(object):
 
     def reset(self, goals=None, mask=None, goal_idx=None):
         """Checkers.reset(goals) for every env (or those where mask != 0).  Returns the output
-        dict (device tensors); reward / local_rewards are not meaningful after a reset."""
+        dict (device tensors); reward / local_rewards are not meaningful after a reset.
+
+        Without goals the selected envs KEEP the goals they have; on the very first reset they get
+        the trainers' default, agent n -> goal n & 1 (np.eye(n_agents) for stage 2,
+        train_offpolicy.py:298)."""
         gi = None
+        if goals is None and goal_idx is None and not self._is_reset:
+            goal_idx = np.arange(self.N, dtype=np.uint8) & 1
         if goal_idx is not None:
             gnp = np.array(np.broadcast_to(np.asarray(goal_idx, dtype=np.uint8), (self.B, self.N)), order="C")
             if gnp.max(initial=0) > 1:
@@ -182,6 +201,17 @@ class VecCheckers(object):
         self._keep = a
         return self.out
 
+    def step_chained(self, actions, out, seed=0, t0=0, auto_reset=True):
+        """One step that may overlap the previous launch on the device (cm3_checkers_step_chained):
+        `actions` is an int8 device tensor [B,N] that was complete before the previous call was
+        made (a slice of a pre-generated stream), `out` a dict of [B,...] (or [1,B,...]) buffers
+        that is not the previous call's - a slot of a rollout ring."""
+        oc = out if isinstance(out, L.CheckersOutputs) else self._outputs_struct(out)
+        L.check(self.lib.cm3_checkers_step_chained(self._h, C.byref(self._st), _ptr(actions), int(seed) & (2**64 - 1),
+                                                   int(t0), 1 if auto_reset else 0, C.byref(oc), self._stream()))
+        self._keep = (actions, oc)
+        return out
+
     def rollout(self, T, actions=None, seed=0, t0=0, auto_reset=False, out=None,
                 record_actions=False):
         """T fused steps in one launch.  actions [T,B,N] or None (device Philox stream keyed
@@ -200,6 +230,27 @@ class VecCheckers(object):
             out = dict(out)
             out["actions"] = rec
         return out
+
+    def plan_rollout(self, T, actions=None, out=None, auto_reset=True, seed=0):
+        """A rollout whose ctypes arguments are built ONCE: the returned callable launches
+        cm3_checkers_rollout(t0) with nothing but the foreign call on the host path (rollout()
+        rebuilds the output struct and re-validates the action tensor on every call).  `actions`
+        must already be an int8 device tensor [T,B,N] (or None for the Philox stream)."""
+        T = int(T)
+        out = self.alloc_outputs(T) if out is None else out
+        if actions is not None and (actions.dtype != torch.int8 or actions.device != self.device
+                                    or tuple(actions.shape) != (T, self.B, self.N) or not actions.is_contiguous()):
+            raise ValueError("plan_rollout needs a contiguous int8 device tensor [T,B,N]")
+        oc = self._outputs_struct(out)
+        fn, h, st, a = self.lib.cm3_checkers_rollout, self._h, C.byref(self._st), _ptr(actions)
+        seed, ar, ocr, dev = int(seed) & (2**64 - 1), 1 if auto_reset else 0, C.byref(oc), self.device
+
+        def launch(t0=0):
+            rc = fn(h, st, a, seed, int(t0), T, ar, None, ocr, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc != 0:
+                L.check(rc)
+        launch.out, launch.keep = out, (actions, oc)
+        return launch
 
     def rollout_gather(self, T, dst_ptrs, dst_B, dst_env0, actions=None, seed=0, t0=0,
                        auto_reset=False):
@@ -241,6 +292,35 @@ class VecCheckers(object):
                                                 _ptr(self._actions_dev), C.byref(self._out_c),
                                                 C.byref(oh), self._stream()))
         return {f: self._host[f].numpy() for f in fields}
+
+    def download(self):
+        """The packed single-step outputs (whatever the last launch wrote to self.out) in ONE
+        device-to-host copy; returns field -> NumPy view of the pinned host mirror."""
+        if self._host is None:
+            self._host = self.alloc_outputs(pinned_host=True)
+            self._host_actions = torch.zeros(self.B, self.N, dtype=torch.int8).pin_memory()
+        self._host.block.copy_(self.out.block, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {f: self._host[f].numpy() for f in FIELDS}
+
+    def rollout_host(self, actions, seed=0, t0=0, auto_reset=True):
+        """T steps with host actions ([T,B,N] int8) and every output delivered to pinned host
+        memory, double buffered (cm3_checkers_rollout_host): the device-to-host copy of step t
+        overlaps the kernel of step t + 1.  Returns field -> NumPy view [T,B,...] (overwritten by
+        the next call with the same T)."""
+        a = np.asarray(actions)
+        T = int(a.shape[0])
+        hr = self._hr.get(T) if hasattr(self, "_hr") else None
+        if hr is None:
+            if not hasattr(self, "_hr"):
+                self._hr = {}
+            hr = self._hr[T] = HostRolloutBuffers(self, T, self._outputs_struct)
+        hr.actions_host.numpy()[...] = _to_int8_host(a, (T, self.B, self.N))
+        L.check(self.lib.cm3_checkers_rollout_host(self._h, C.byref(self._st), _ptr(hr.actions_host), _ptr(hr.actions_dev), T,
+                                                  int(seed) & (2**64 - 1), int(t0), 1 if auto_reset else 0, hr.outs_c,
+                                                  hr.blocks_c, _ptr(hr.host), hr.block_bytes, hr.block_bytes,
+                                                  self._stream()))
+        return hr.views
 
     # ------------------------------------------------------------------ state
     def get_state_host(self):

@@ -8,10 +8,13 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from ._buffers import alloc_fields, _to_int8_host
+from ._buffers import HostRolloutBuffers, alloc_fields, _to_int8_host
 
 FIELDS = L.ParticleOutputs.FIELDS
 OBS_FIELDS = ("global_state", "obs_others", "obs_self")
+# the fields of the reference's return tuple (multiagent/environment.py:123); `collisions`
+# (scenario.collisions latched per step) is this library's extra
+REF_FIELDS = ("global_state", "obs_others", "obs_self", "reward", "reward_n", "done")
 
 
 def _ptr(t):
@@ -64,6 +67,8 @@ class VecParticle(object):
         h = C.c_void_p()
         L.check(self.lib.cm3_particle_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        tiles = C.c_int32(0)
+        L.check(self.lib.cm3_particle_tiles(h, C.byref(tiles)))
 
         dev = self.device
         B, N = self.B, self.N
@@ -73,8 +78,10 @@ class VecParticle(object):
             steps=torch.zeros(B, dtype=torch.int32, device=dev),
             collisions=torch.zeros(B, dtype=torch.int32, device=dev),
             reached=torch.zeros(B, dtype=torch.uint8, device=dev))
-        self._st = L.ParticleState(*[_ptr(self.state[k]) for k in
-                                     ("sv", "landmarks", "steps", "collisions", "reached")])
+        # per-tile launch-chaining words (cm3_particle_state.sync); not env state: never saved
+        self._sync = torch.zeros(2, tiles.value, dtype=torch.int32, device=dev)
+        self._st = L.ParticleState(*([_ptr(self.state[k]) for k in
+                                      ("sv", "landmarks", "steps", "collisions", "reached")] + [_ptr(self._sync)]))
         self.out = self.alloc_outputs()
         self._out_c = self._outputs_struct(self.out)
         self._actions_dev = torch.zeros(B, N, dtype=torch.int8, device=dev)
@@ -85,29 +92,31 @@ class VecParticle(object):
     def field_shapes(self):
         B, N = self.B, self.N
         return dict(global_state=(B, N, 4), obs_others=(B, N, self.L_others), obs_self=(B, N, 4),
-                    reward=(B,), reward_n=(B, N), done=(B,))
+                    reward=(B,), reward_n=(B, N), done=(B,), collisions=(B,), reached=(B,))
 
-    def bytes_per_env_step(self):
+    def bytes_per_env_step(self, fields=None):
         """Algorithmic bytes of one env-step."""
         el = 8 if self.dtype == torch.float64 else 4
         N = self.N
-        out = sum(int(np.prod(s[1:])) for k, s in self.field_shapes().items() if k != "done") * el + 1
         state = 2 * (4 * N * el) + 2 * N * el + 2 * 4 + 2 * 4 + 2  # sv rw, landmarks r, steps rw, collisions rw, reached rw
-        return out + state + N
+        return self.out_bytes_per_env_step(fields) + state + N
 
     def field_dtype(self, k):
-        return torch.uint8 if k == "done" else self.dtype
+        return torch.uint8 if k in ("done", "reached") else torch.int32 if k == "collisions" else self.dtype
 
-    def out_bytes_per_env_step(self):
-        return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items())
+    def out_bytes_per_env_step(self, fields=None):
+        """Output bytes per env-step of the reference's return tuple (REF_FIELDS) or of `fields`."""
+        fields = REF_FIELDS if fields is None else fields
+        return sum(int(np.prod(s[1:])) * self.field_dtype(k).itemsize for k, s in self.field_shapes().items() if k in fields)
 
-    def alloc_outputs(self, T=None, pinned_host=False):
-        """Zeroed output buffers: [B, ...] per field (T=None) or [T, B, ...] rollout buffers.  The
-        single-step set of a batch that is a multiple of 32 envs is one packed allocation (every
-        field stays 16-byte aligned), so that step_host needs a single device-to-host copy."""
+    def alloc_outputs(self, T=None, pinned_host=False, fields=None):
+        """Zeroed output buffers: [B, ...] per field (T=None) or [T, B, ...] rollout buffers, for
+        every field or for `fields`.  The single-step set is one packed allocation (every field
+        16-byte aligned), so that step_host needs a single device-to-host copy."""
         lead = () if T is None else (int(T),)
-        return alloc_fields(self.field_shapes(), self.field_dtype, lead, device=self.device,
-                            pinned=pinned_host, packed=T is None and self.B % 32 == 0)
+        shapes = {k: v for k, v in self.field_shapes().items() if fields is None or k in fields}
+        return alloc_fields(shapes, self.field_dtype, lead, device=self.device,
+                            pinned=pinned_host, packed=T is None)
 
     @staticmethod
     def _outputs_struct(out):
@@ -168,6 +177,33 @@ class VecParticle(object):
         self._keep = a
         return self.out
 
+    def step_chained(self, actions, out, seed=0, t0=0, auto_reset=True):
+        """One step that may overlap the previous launch on the device (cm3_particle_step_chained);
+        see VecCheckers.step_chained for the contract on `actions` and `out`."""
+        oc = out if isinstance(out, L.ParticleOutputs) else self._outputs_struct(out)
+        L.check(self.lib.cm3_particle_step_chained(self._h, C.byref(self._st), _ptr(actions), int(seed) & (2**64 - 1),
+                                                   int(t0), 1 if auto_reset else 0, C.byref(oc), self._stream()))
+        self._keep = (actions, oc)
+        return out
+
+    def plan_rollout(self, T, actions=None, out=None, auto_reset=True, seed=0):
+        """See VecCheckers.plan_rollout: a rollout launch with its ctypes arguments built once."""
+        T = int(T)
+        out = self.alloc_outputs(T) if out is None else out
+        if actions is not None and (actions.dtype != torch.int8 or actions.device != self.device
+                                    or tuple(actions.shape) != (T, self.B, self.N) or not actions.is_contiguous()):
+            raise ValueError("plan_rollout needs a contiguous int8 device tensor [T,B,N]")
+        oc = self._outputs_struct(out)
+        fn, h, st, a = self.lib.cm3_particle_rollout, self._h, C.byref(self._st), _ptr(actions)
+        seed, ar, ocr, dev = int(seed) & (2**64 - 1), 1 if auto_reset else 0, C.byref(oc), self.device
+
+        def launch(t0=0):
+            rc = fn(h, st, a, seed, int(t0), T, ar, None, ocr, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc != 0:
+                L.check(rc)
+        launch.out, launch.keep = out, (actions, oc)
+        return launch
+
     def rollout(self, T, actions=None, seed=0, t0=0, auto_reset=False, out=None,
                 record_actions=False):
         T = int(T)
@@ -225,6 +261,35 @@ class VecParticle(object):
                                                 _ptr(self._actions_dev), C.byref(self._out_c),
                                                 C.byref(oh), self._stream()))
         return {f: self._host[f].numpy() for f in fields}
+
+    def download(self):
+        """The packed single-step outputs (whatever the last launch wrote to self.out) in ONE
+        device-to-host copy; returns field -> NumPy view of the pinned host mirror."""
+        if self._host is None:
+            self._host = self.alloc_outputs(pinned_host=True)
+            self._host_actions = torch.zeros(self.B, self.N, dtype=torch.int8).pin_memory()
+        self._host.block.copy_(self.out.block, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {f: self._host[f].numpy() for f in FIELDS}
+
+    def rollout_host(self, actions, seed=0, t0=0, auto_reset=True):
+        """T steps with host actions ([T,B,N] int8) and every output delivered to pinned host
+        memory, double buffered (cm3_particle_rollout_host): the device-to-host copy of step t
+        overlaps the kernel of step t + 1.  Returns field -> NumPy view [T,B,...] (overwritten by
+        the next call with the same T)."""
+        a = np.asarray(actions)
+        T = int(a.shape[0])
+        hr = self._hr.get(T) if hasattr(self, "_hr") else None
+        if hr is None:
+            if not hasattr(self, "_hr"):
+                self._hr = {}
+            hr = self._hr[T] = HostRolloutBuffers(self, T, self._outputs_struct)
+        hr.actions_host.numpy()[...] = _to_int8_host(a, (T, self.B, self.N))
+        L.check(self.lib.cm3_particle_rollout_host(self._h, C.byref(self._st), _ptr(hr.actions_host), _ptr(hr.actions_dev), T,
+                                                  int(seed) & (2**64 - 1), int(t0), 1 if auto_reset else 0, hr.outs_c,
+                                                  hr.blocks_c, _ptr(hr.host), hr.block_bytes, hr.block_bytes,
+                                                  self._stream()))
+        return hr.views
 
     # ------------------------------------------------------------------ state
     def get_state_host(self):

@@ -36,8 +36,8 @@
 extern "C" {
 #endif
 
-#define CM3_ABI_VERSION 1
-#define CM3_MAX_AGENTS 4
+#define CM3_ABI_VERSION 2
+#define CM3_MAX_AGENTS 8
 #define CM3_MAX_DST 8 /* destination buffer sets of *_rollout_gather (GPUs of one NVSwitch node) */
 
 typedef enum {
@@ -45,7 +45,7 @@ typedef enum {
     CM3_ERR_BAD_ARG = -1,     /* NULL handle / pointer, bad enum, bad mask */
     CM3_ERR_BAD_SHAPE = -2,   /* geometry the reference itself rejects (checkers.py:16-17) */
     CM3_ERR_CUDA = -3,        /* a CUDA runtime call failed; message has the CUDA error */
-    CM3_ERR_UNSUPPORTED = -4, /* geometry / agent count without a compiled kernel */
+    CM3_ERR_UNSUPPORTED = -4, /* geometry / agent count outside what the kernels address */
     CM3_ERR_NO_DEVICE = -5    /* no CUDA device: there is no CPU fallback */
 } cm3_status;
 
@@ -75,7 +75,18 @@ typedef struct {
     int32_t tile;          /* cm3_tile of grid / obs_self_t (CM3_TILE_I8 needs real == F32) */
     int64_t env_id_offset; /* global id of local env 0 (keys the Philox streams, so results
                               do not depend on how the batch is sharded over GPUs) */
+    int32_t random_goal;   /* n_agents == 1 only: 1 = an in-kernel episode reset (auto_reset) draws
+                              the new episode's goal uniformly from {0, 1} like the trainer does
+                              before every episode (alg/train_offpolicy.py:291-296), from Philox keyed
+                              by (seed; global env id, step); 0 = the goal is kept */
+    int32_t reserved;
 } cm3_checkers_config;
+
+/* Any board the reference's constructor accepts (n_rows odd, n_columns even, checkers.py:16-17) is
+ * accepted as DATA as long as the bitboards can address it: n_rows * n_columns <= 64,
+ * n_columns + 2 * n_obs + 1 <= 32, 1 <= n_obs <= 3, n_rows + 2 * n_obs <= 16, n_agents <= 8.  The
+ * boards of the reference's configs (3 x 8 and 3 x 16, n_obs 2) additionally have kernels with the
+ * geometry compiled in. */
 
 /* Compact per-env state (device pointers, caller-owned):
  *   remaining[b]  bit i*n_columns+j set <=> valid-grid cell (i,j) still holds its reward
@@ -86,6 +97,9 @@ typedef struct {
     uint64_t *remaining; /* [B]    */
     uint32_t *agents;    /* [B][N] */
     uint32_t *meta;      /* [B]    */
+    uint32_t *sync;      /* [2][cm3_checkers_tiles(h)] launch-chaining words, zero-initialised by the
+                            caller and otherwise opaque; NULL = launches are ordered by the stream
+                            alone and *_step_chained is refused (see cm3_checkers_step_chained) */
 } cm3_checkers_state;
 
 /* Outputs of reset/step (env/checkers.py:262,291), dense per field.  For rollouts every
@@ -99,16 +113,23 @@ typedef struct {
     void *reward;        /* [B]                            Real  np.sum(local_rewards) :243 */
     void *local_rewards; /* [B][N]                         Real  :232-237 */
     uint8_t *done;       /* [B]                                  :246-260 */
+    uint8_t *goal_idx;   /* [B][N] goal index of every agent in the episode the written observations
+                            belong to (the trainers carry `goals` beside every transition,
+                            train_offpolicy.py:291-298; with cfg.random_goal it changes at in-kernel
+                            resets).  Optional like every field. */
 } cm3_checkers_outputs;
 
 typedef struct cm3_checkers_s *cm3_checkers_t;
 
 int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out);
 int cm3_checkers_destroy(cm3_checkers_t h);
+/* number of env tiles (one warp each) a launch of this handle is cut into: the length of one row of
+ * cm3_checkers_state.sync */
+int cm3_checkers_tiles(cm3_checkers_t h, int32_t *tiles);
 
 /* Checkers.reset(goals) for the envs selected by env_mask (NULL = all).  goal_idx is
  * [B][N] uint8 on the device, goal_idx[b][n] = argmax(goals[n]) in {0,1} (checkers.py:235);
- * NULL = agent n gets goal n & 1 (np.eye(n_agents) for N = 2, train_offpolicy.py:298).
+ * NULL = every selected env keeps the goals it already has (zeroed state: goal 0 for everyone).
  * Observations of ALL envs are written to outs (fresh for reset envs, current otherwise);
  * reward / local_rewards are not touched, done is written as 0 for the reset envs. */
 int cm3_checkers_reset(cm3_checkers_t h, const cm3_checkers_state *st, const uint8_t *goal_idx,
@@ -124,13 +145,29 @@ int cm3_checkers_step(cm3_checkers_t h, const cm3_checkers_state *st, const int8
  *                device from Philox4x32-10 keyed by (seed; global env id, t0 + t)
  *   actions_out  [T][B][N] int8 device or NULL: the actions that were applied
  *   auto_reset   0: reference behaviour (keeps stepping past done)
- *                1: an env whose step returned done is reset inside the kernel (same goals)
+ *                1: an env whose step returned done is reset inside the kernel (same goals,
+ *                   or a fresh goal when cfg.random_goal is set)
  *                   and the observations written for that step are those of the fresh
  *                   episode; reward / done still describe the terminal transition
  *   outs         [T][B][...] per field */
 int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
                          uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
                          int8_t *actions_out, const cm3_checkers_outputs *outs, void *stream);
+
+/* One step that may OVERLAP the previous launch on this state (policy-free inner loops, e.g. a
+ * pre-generated or double-buffered action stream; alg/train_onpolicy.py:302-350 with the policy's
+ * actions already in HBM).  Consecutive launches on one state depend on each other tile by tile -
+ * tile i of step k + 1 needs tile i of step k - and that is all a chained launch waits for (ticket
+ * words in st->sync, acquire / release), instead of the completion of the whole previous grid as
+ * stream order would have it: the store phase of step k overlaps the compute phase of step k + 1.
+ * Contract: (1) st->sync non-NULL; (2) `actions` was complete in memory before the PREVIOUS launch
+ * on this stream was enqueued, or is written by a kernel that sits between the two step launches
+ * in the stream (that kernel then orders everything, as usual); (3) `outs` does not alias the
+ * previous launch's outs (use a ring of >= 2 slots).  auto_reset as in cm3_checkers_rollout
+ * (seed / t0 key the goal redraw when cfg.random_goal is set). */
+int cm3_checkers_step_chained(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
+                              uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_checkers_outputs *outs, void *stream);
 
 /* Fused rollout + all-gather.  Same computation as cm3_checkers_rollout, but every output element
  * is stored to n_dst destination buffer sets instead of one.  Each set is laid out
@@ -179,6 +216,21 @@ int cm3_checkers_step_host_packed(cm3_checkers_t h, const cm3_checkers_state *st
                                   const cm3_checkers_outputs *outs_dev, const void *dev_block,
                                   void *host_block, size_t block_bytes, void *stream);
 
+/* Host-buffer rollout, double buffered: T steps whose actions come from host memory and whose
+ * outputs all land in host memory, with the device-to-host copy of step t overlapping the kernel of
+ * step t + 1.  Per step t: copy actions_host[t] ([B][N]) to actions_dev[t & 1], step (one launch,
+ * in-kernel episode reset if auto_reset), then copy the packed output block dev_blocks[t & 1]
+ * (block_bytes; outs_dev[t & 1] are the field pointers inside it, see *_step_host_packed) to
+ * host_blocks + t * host_stride on a second stream owned by the handle.  Returns after the last copy
+ * has landed.  Pinned host memory makes the copies asynchronous.  This is the loop a host-side
+ * trainer with a pre-drawn action sequence runs (the trainers' pre-training phase draws
+ * np.random.randint actions, alg/train_onpolicy.py:305-307), at the PCIe rate of the outputs instead
+ * of copy + kernel + copy in series. */
+int cm3_checkers_rollout_host(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions_host,
+                              int8_t *actions_dev, int32_t T, uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_checkers_outputs *outs_dev, const void *const *dev_blocks,
+                              void *host_blocks, size_t block_bytes, size_t host_stride, void *stream);
+
 /* ------------------------------------------------------------------ Particle */
 
 /* World / scenario constants (defaults = the reference's, filled by
@@ -216,6 +268,7 @@ typedef struct {
     int32_t *steps;      /* [B]  env.steps */
     int32_t *collisions; /* [B]  scenario.collisions (episode total, double counted :135-137) */
     uint8_t *reached;    /* [B]  bit n = agents[n].reached */
+    uint32_t *sync;      /* [2][cm3_particle_tiles(h)], see cm3_checkers_state.sync */
 } cm3_particle_state;
 
 typedef struct {
@@ -225,12 +278,20 @@ typedef struct {
     void *reward;       /* [B]                    Real np.sum(reward_n), environment.py:107 */
     void *reward_n;     /* [B][N]                 Real multi-goal_spread.py:121-138 */
     uint8_t *done;      /* [B]                         environment.py:118-121 */
+    int32_t *collisions; /* [B] scenario.collisions after this step, BEFORE an in-kernel reset zeroes
+                            it: at a step with done = 1 it is the finished episode's total, which is
+                            what the trainer's good / bad episode split reads
+                            (alg/train_onpolicy.py:356).  Optional like every field. */
+    uint8_t *reached;    /* [B] bit n = agents[n].reached after this step (multi-goal_spread.py:126-129),
+                            what Scenario.done(agent) returns (:140-143); before an in-kernel reset
+                            clears it.  Optional. */
 } cm3_particle_outputs;
 
 typedef struct cm3_particle_s *cm3_particle_t;
 
 int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out);
 int cm3_particle_destroy(cm3_particle_t h);
+int cm3_particle_tiles(cm3_particle_t h, int32_t *tiles);
 
 /* MultiAgentEnv.reset() for the envs selected by env_mask (NULL = all).
  *   init_pos / init_landmarks  [B][N][2] Real device: the state reset_world() produced on the
@@ -250,10 +311,16 @@ int cm3_particle_step(cm3_particle_t h, const cm3_particle_state *st, const int8
                       const cm3_particle_outputs *outs, void *stream);
 
 /* T fused steps; same contract as cm3_checkers_rollout.  With auto_reset the fresh episode is
- * drawn as in cm3_particle_reset with reset_counter = t0 + t + 1. */
+ * drawn as in cm3_particle_reset, keyed by (seed; global env id, t0 + t + 1) in a counter domain of
+ * its own (explicit resets and in-kernel resets never share a Philox counter). */
 int cm3_particle_rollout(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
                          uint64_t seed, int64_t t0, int32_t T, int32_t auto_reset,
                          int8_t *actions_out, const cm3_particle_outputs *outs, void *stream);
+
+/* see cm3_checkers_step_chained; seed / t0 key the in-kernel reset draws */
+int cm3_particle_step_chained(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
+                              uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_particle_outputs *outs, void *stream);
 
 /* Fused rollout + all-gather; see cm3_checkers_rollout_gather. */
 int cm3_particle_rollout_gather(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions,
@@ -278,6 +345,12 @@ int cm3_particle_step_host_packed(cm3_particle_t h, const cm3_particle_state *st
                                   const int8_t *actions_host, int8_t *actions_dev,
                                   const cm3_particle_outputs *outs_dev, const void *dev_block,
                                   void *host_block, size_t block_bytes, void *stream);
+
+/* see cm3_checkers_rollout_host */
+int cm3_particle_rollout_host(cm3_particle_t h, const cm3_particle_state *st, const int8_t *actions_host,
+                              int8_t *actions_dev, int32_t T, uint64_t seed, int64_t t0, int32_t auto_reset,
+                              const cm3_particle_outputs *outs_dev, const void *const *dev_blocks,
+                              void *host_blocks, size_t block_bytes, size_t host_stride, void *stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ def header_functions():
 def test_library_builds_and_loads():
     cm3_b200.build_library()
     lib = L.load_library()
-    assert lib.cm3_abi_version() == 1
+    assert lib.cm3_abi_version() == L.ABI_VERSION == 2
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -37,12 +37,12 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_struct_sizes_match_header():
     # natural alignment, no packing: sizes derived by hand from include/cm3env.h
-    assert C.sizeof(L.CheckersConfig) == 5 * 4 + 2 * 16 + 4 * 4 + 4 + 8  # padded to 8
-    assert C.sizeof(L.CheckersState) == 24
-    assert C.sizeof(L.CheckersOutputs) == 64
-    assert C.sizeof(L.ParticleConfig) == 6 * 4 + 8 + 8 * 8 + 4 * 32 + 16
-    assert C.sizeof(L.ParticleState) == 40
-    assert C.sizeof(L.ParticleOutputs) == 48
+    assert C.sizeof(L.CheckersConfig) == 5 * 4 + 2 * 32 + 4 * 4 + 4 + 8 + 8  # padded to 8
+    assert C.sizeof(L.CheckersState) == 32
+    assert C.sizeof(L.CheckersOutputs) == 72
+    assert C.sizeof(L.ParticleConfig) == 6 * 4 + 8 + 8 * 8 + 4 * 64 + 16
+    assert C.sizeof(L.ParticleState) == 48
+    assert C.sizeof(L.ParticleOutputs) == 64
 
 
 def test_header_is_plain_c_and_layouts_match_the_ctypes_binding(tmp_path):
@@ -91,7 +91,12 @@ def test_bad_geometry_is_rejected_like_the_reference():
     assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -2  # checkers.py:17
     assert b"odd" in lib.cm3_last_error()
     cfg = L.CheckersConfig(n_rows=7, n_columns=30, n_obs=2, n_agents=2, max_steps=33, num_envs=4)
-    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -4  # no compiled kernel
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -4  # 210 cells: beyond the 64-bit bitboard
+    assert b"bitboards" in lib.cm3_last_error()
+    cfg = L.CheckersConfig(n_rows=3, n_columns=8, n_obs=2, n_agents=1, max_steps=33, num_envs=4, random_goal=2)
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -1
+    cfg = L.CheckersConfig(n_rows=3, n_columns=8, n_obs=2, n_agents=2, max_steps=33, num_envs=4, random_goal=1)
+    assert lib.cm3_checkers_create(C.byref(cfg), C.byref(h)) == -1  # the goal redraw is the stage-1 protocol
 
 
 def test_null_arguments():

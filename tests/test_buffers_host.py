@@ -17,7 +17,10 @@ def test_packed_fields_are_gapless_aligned_views_of_one_block():
     assert isinstance(out, FieldDict) and out.block is not None and list(out) == list(SHAPES)
     base = out.block.data_ptr()
     spans = sorted((v.data_ptr() - base, v.numel() * v.element_size(), k) for k, v in out.items())
-    assert spans[0][0] == 0 and sum(n for _, n, _ in spans) == out.block.numel()
+    used = sum(n for _, n, _ in spans)
+    # gapless fields, then padding to a multiple of 256 bytes (blocks are stacked by rollout_host)
+    assert spans[0][0] == 0 and out.block.numel() == (used + 255) // 256 * 256
+    assert out.offsets == {k: off for off, _, k in spans}
     for (o0, n0, _), (o1, _, _) in zip(spans, spans[1:]):
         assert o0 + n0 == o1                      # back to back: the block is exactly the fields
     for k, v in out.items():

@@ -1,0 +1,427 @@
+"""GPU parity tests for what round 2 added, all through the C ABI:
+
+* chained single-step launches (cm3_*_step_chained: per-tile ticket words instead of a grid-wide
+  dependency) == plain stream-ordered steps, directly and replayed from a CUDA graph;
+* board geometry as data (any board the bitboards address) and 5..8 agents, Checkers and particle,
+  bit-exact / 1e-5 against the oracle;
+* stage-1 goal redraw on in-kernel reset (train_offpolicy.py:291-296) against the CPU Philox twin;
+* masked resets keep the goals of the envs they touch;
+* the `goal_idx`, `collisions` and `reached` output fields;
+* the double-buffered host rollout (cm3_*_rollout_host) == a sequence of device steps;
+* planned rollouts == rollout().
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import oracle
+from cm3_b200 import VecCheckers, VecParticle, presets
+from cm3_b200.vec_checkers import REF_FIELDS as CK_REF
+from cm3_b200.vec_particle import REF_FIELDS as PT_REF
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CK2 = dict(presets.CHECKERS["stage2"], max_steps=presets.MAX_STEPS)
+CK1 = dict(presets.CHECKERS["stage1"], max_steps=presets.MAX_STEPS)
+ANTI = presets.PARTICLE["antipodal"]
+MERGE = presets.PARTICLE["merge"]
+
+
+def _np(x):
+    return x.cpu().numpy() if torch.is_tensor(x) else x
+
+
+# ---------------------------------------------------------------------------------- chained steps
+@pytest.mark.parametrize("B", [4096, 1000])
+@pytest.mark.parametrize("game", ["ck2", "ck1", "pa4", "pm2"])
+def test_chained_steps_equal_stream_ordered_steps(game, B):
+    """T chained launches into a ring of output slots - issued directly and replayed from a CUDA
+    graph (the ticket words make the chain replay-safe) - produce exactly what T plain launches
+    produce, field by field, and leave the same state."""
+    T, ring = 70, 35
+    rng = np.random.default_rng(B)
+
+    def make():
+        if game.startswith("ck"):
+            e = VecCheckers(B, **(CK2 if game == "ck2" else CK1))
+            e.reset(goals=np.eye(2) if game == "ck2" else np.array([[0, 1]]))
+        else:
+            n, cfg = (4, ANTI) if game == "pa4" else (2, MERGE)
+            e = VecParticle(B, n, cfg, max_steps=presets.MAX_STEPS)
+            e.reset(seed=3)
+        return e
+    a, b, c = make(), make(), make()
+    fields = CK_REF if game.startswith("ck") else PT_REF
+    actions = torch.from_numpy(rng.integers(0, 5, size=(T, B, a.N)).astype(np.int8)).to(a.device)
+    # reference: plain steps (T = 1 rollouts so that the in-kernel reset matches)
+    want = a.alloc_outputs(T, fields=fields)
+    for t in range(T):
+        a.rollout(1, actions=actions[t:t + 1], auto_reset=True, t0=t, seed=5, out={k: v[t:t + 1] for k, v in want.items()})
+    # chained, issued directly
+    got = b.alloc_outputs(T, fields=fields)
+    for t in range(T):
+        b.step_chained(actions[t], {k: v[t] for k, v in got.items()}, seed=5, t0=t, auto_reset=True)
+    torch.cuda.synchronize()
+    for f in fields:
+        assert torch.equal(got[f], want[f]), (game, f)
+    for k in a.state:
+        assert torch.equal(a.state[k], b.state[k]), k
+    # chained, from a CUDA graph of `ring` launches replayed twice
+    slots = c.alloc_outputs(ring, fields=fields)
+    acts = [actions[t] for t in range(ring)]
+    outs = [c._outputs_struct({k: v[t] for k, v in slots.items()}) for t in range(ring)]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        c.step_chained(acts[0], outs[0], seed=5, t0=0, auto_reset=True)   # warm-up outside capture
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    c.load_state_dict(make().state_dict())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for t in range(ring):
+            c.step_chained(acts[t], outs[t], seed=5, t0=t, auto_reset=True)
+    if game.startswith("ck"):
+        # Checkers consumes no randomness on reset: the second replay continues the same trajectory
+        # with the first `ring` actions again
+        d = make()
+        ref = d.alloc_outputs(ring, fields=fields)
+        for rep in range(2):
+            g.replay()
+            for t in range(ring):
+                d.rollout(1, actions=actions[t:t + 1], auto_reset=True, out={k: v[t:t + 1] for k, v in ref.items()})
+            torch.cuda.synchronize()
+            for f in fields:
+                assert torch.equal(slots[f], ref[f]), (game, "replay %d" % rep, f)
+    else:
+        g.replay()
+        torch.cuda.synchronize()
+        for f in fields:
+            assert torch.equal(slots[f], want[f][:ring]), (game, f)
+
+
+def test_chained_needs_sync_words():
+    import ctypes as C
+    from cm3_b200 import _lib as L
+    env = VecCheckers(64, **CK2)
+    env.reset(goals=np.eye(2))
+    st = L.CheckersState(env._st.remaining, env._st.agents, env._st.meta, None)
+    a = torch.zeros(64, 2, dtype=torch.int8, device=env.device)
+    rc = env.lib.cm3_checkers_step_chained(env._h, C.byref(st), C.c_void_p(a.data_ptr()), 0, 0, 1, C.byref(env._out_c), env._stream())
+    assert rc == -1 and b"sync" in env.lib.cm3_last_error()
+    # without sync words the plain entry points still work (stream order alone)
+    L.check(env.lib.cm3_checkers_step(env._h, C.byref(st), C.c_void_p(a.data_ptr()), C.byref(env._out_c), env._stream()))
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------- geometry as data, many agents
+def _run_ck(B, ctor, T, seed, dtype=torch.float32, **kw):
+    rng = np.random.default_rng(seed)
+    N = ctor["n_agents"]
+    actions = rng.integers(0, 5, size=(T, B, N)).astype(np.int8)
+    actions[rng.random(actions.shape) < 0.02] = -3
+    goal_idx = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
+    orc = oracle.OracleCheckers(B, nthreads=oracle.max_threads(), **ctor)
+    env = VecCheckers(B, dtype=dtype, **ctor, **kw)
+    cast = np.float32 if dtype == torch.float32 else np.float64
+    ref, out = orc.reset(goal_idx), env.reset(goal_idx=goal_idx)
+    obs = ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "done")
+    for f in obs:
+        np.testing.assert_array_equal(_np(out[f]), ref[f] if f == "done" else ref[f].astype(cast), err_msg="reset " + f)
+    for t in range(T):
+        ref, out = orc.step(actions[t]), env.step(actions[t])
+        for f in gu.CHECKERS_FIELDS:
+            np.testing.assert_array_equal(_np(out[f]), ref[f] if f == "done" else ref[f].astype(cast), err_msg="t=%d %s" % (t, f))
+        np.testing.assert_array_equal(_np(out["goal_idx"]), goal_idx)
+    # the fused rollout takes the same kernels through their multi-step path
+    env.reset(goal_idx=goal_idx)
+    orc.reset(goal_idx)
+    ro = env.rollout(T, actions=actions)
+    for t in range(T):
+        ref = orc.step(actions[t])
+        for f in gu.CHECKERS_FIELDS:
+            np.testing.assert_array_equal(_np(ro[f][t]), ref[f] if f == "done" else ref[f].astype(cast), err_msg="rollout t=%d %s" % (t, f))
+
+
+@pytest.mark.parametrize("geom", [(7, 8, 2), (5, 12, 3), (9, 6, 1), (1, 2, 1), (3, 20, 2), (3, 2, 2)])
+@pytest.mark.parametrize("N", [1, 2, 3])
+def test_any_board_the_bitboards_address(geom, N):
+    """Boards that never had a compiled kernel: the geometry travels as data (checkers.py:5-35)."""
+    R, Cc, O = geom
+    if N == 1 and R < 3:
+        pytest.skip("stage-1 start row 2 needs three rows (checkers.py:276)")
+    rows = [0, R - 1, R // 2][:N]
+    cols = [Cc, Cc, Cc - 1][:N] if R == 1 else [Cc, Cc, Cc][:N]
+    if R == 1:
+        rows = [0, 0, 0][:N]
+        cols = [Cc, Cc - 1, Cc - 2][:N]
+        if Cc - (N - 1) < 0:
+            pytest.skip("board too small for %d agents" % N)
+    ctor = dict(n_rows=R, n_columns=Cc, n_obs=O, agents_r=rows, agents_c=cols, n_agents=N, max_steps=60)
+    _run_ck(97, ctor, 64, seed=R * 1000 + Cc * 10 + N)
+
+
+@pytest.mark.parametrize("N", [5, 6, 7, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_checkers_up_to_eight_agents(N, dtype):
+    ctor = dict(n_rows=5, n_columns=8, n_obs=2, agents_r=[0, 4, 1, 3, 2, 0, 4, 2][:N], agents_c=[8, 8, 8, 8, 8, 7, 7, 7][:N],
+                n_agents=N, max_steps=50)
+    _run_ck(70, ctor, 55, seed=N, dtype=dtype)
+
+
+def test_checkers_int8_tiles_dynamic_geometry():
+    ctor = dict(n_rows=5, n_columns=10, n_obs=3, agents_r=[0, 4], agents_c=[10, 10], n_agents=2, max_steps=50)
+    rng = np.random.default_rng(2)
+    B, T = 200, 40
+    actions = rng.integers(0, 5, size=(T, B, 2)).astype(np.int8)
+    a, b = VecCheckers(B, **ctor), VecCheckers(B, tile_dtype=torch.int8, **ctor)
+    a.reset(goals=np.eye(2)); b.reset(goals=np.eye(2))
+    ra, rb = a.rollout(T, actions=actions, auto_reset=True), b.rollout(T, actions=actions, auto_reset=True)
+    for f in gu.CHECKERS_FIELDS:
+        want = ra[f].to(torch.int8) if f in ("grid", "obs_self_t") else ra[f]
+        assert torch.equal(rb[f], want), f
+
+
+def test_static_and_dynamic_kernels_agree():
+    """The stage-1 / stage-2 boards through the geometry-as-data kernels (CM3_CK_DYNAMIC=1 in a
+    child process) against the oracle: same bar as the compiled-in geometry."""
+    code = r"""
+import sys
+sys.path[:0] = [%r, %r, %r]
+import numpy as np, torch, oracle, golden_util as gu
+from cm3_b200 import VecCheckers, presets
+for key, B in (("stage2", 530), ("stage1", 333)):
+    ctor = dict(presets.CHECKERS[key], max_steps=33)
+    N = ctor["n_agents"]
+    rng = np.random.default_rng(B)
+    acts = rng.integers(0, 5, size=(50, B, N)).astype(np.int8)
+    gi = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
+    env, orc = VecCheckers(B, **ctor), oracle.OracleCheckers(B, **ctor)
+    env.reset(goal_idx=gi); orc.reset(gi)
+    ro = env.rollout(50, actions=acts)
+    for t in range(50):
+        ref = orc.step(acts[t])
+        for f in gu.CHECKERS_FIELDS:
+            want = ref[f] if f == "done" else ref[f].astype(np.float32)
+            assert np.array_equal(ro[f][t].cpu().numpy(), want), (key, t, f)
+print("dynamic ok")
+""" % (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"))
+    env = dict(os.environ, CM3_CK_DYNAMIC="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "dynamic ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("N", [5, 6, 7, 8])
+def test_particle_up_to_eight_agents(N):
+    """Teacher-forced float32 (1e-5, north_star's bar) and free-running float64 (1e-9) against the
+    oracle for agent counts the reference's make_world accepts (multi-goal_spread.py:36-37)."""
+    B, T = 96, 40
+    rng = np.random.default_rng(N)
+    ang = np.arange(N) * 2 * np.pi / N
+    cfg = dict(n_agents=N, agents_x=list(0.8 * np.cos(ang)), agents_y=list(0.8 * np.sin(ang)),
+               landmarks_x=list(-0.8 * np.cos(ang)), landmarks_y=list(-0.8 * np.sin(ang)), initial_std=0)
+    pos = np.tile(np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1), (B, 1, 1)) + rng.normal(0, 0.05, size=(B, N, 2))
+    lm = np.tile(np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1), (B, 1, 1))
+    # goal-seeking actions: everyone crosses the centre, plenty of contacts
+    def policy(st):
+        d = lm - st["pos"]
+        horiz = np.abs(d[..., 0]) > np.abs(d[..., 1])
+        a = np.where(horiz, np.where(d[..., 0] > 0, 2, 1), np.where(d[..., 1] > 0, 4, 3))
+        return np.where(rng.random(a.shape) < 0.2, rng.integers(0, 5, size=a.shape), a).astype(np.int8)
+    po = oracle.OracleParticle(B, N, max_steps=T + 5)
+    e64 = VecParticle(B, N, cfg, max_steps=T + 5, dtype=torch.float64)
+    e32 = VecParticle(B, N, cfg, max_steps=T + 5)
+    po.reset_to(pos, lm)
+    e64.reset(init_pos=pos, init_landmarks=lm)
+    contacts = 0
+    for t in range(T):
+        st = po.get_state()
+        a = policy(st)
+        e32.set_state(pos=st["pos"], vel=st["vel"], landmarks=st["landmarks"], steps=st["steps"],
+                      collisions=st["collisions"], reached=st["reached"])
+        ref = {k: v.copy() for k, v in po.step(a).items()}
+        o32, o64 = e32.step(a), e64.step(a)
+        for f in ("global_state", "obs_others", "obs_self", "reward", "reward_n"):
+            np.testing.assert_allclose(_np(o32[f]), ref[f], rtol=1e-5, atol=1e-6, err_msg="f32 t=%d %s" % (t, f))
+            np.testing.assert_allclose(_np(o64[f]), ref[f], rtol=1e-9, atol=1e-11, err_msg="f64 t=%d %s" % (t, f))
+        np.testing.assert_array_equal(_np(o64["done"]), ref["done"])
+        np.testing.assert_array_equal(_np(o64["collisions"]), po.get_state()["collisions"])
+        contacts += int(po.get_state()["collisions"].sum())
+    assert contacts > 0
+
+
+# ---------------------------------------------------------------------------------- goals
+def test_masked_reset_keeps_goals_and_first_reset_defaults():
+    """a reset without goals must not overwrite the goals of the envs it touches."""
+    B = 64
+    env = VecCheckers(B, **CK2)
+    out = env.reset()                                  # first reset: agent n -> goal n & 1
+    np.testing.assert_array_equal(_np(out["goal_idx"]), np.tile([0, 1], (B, 1)))
+    gi = np.random.default_rng(0).integers(0, 2, size=(B, 2)).astype(np.uint8)
+    env.reset(goal_idx=gi)
+    mask = np.zeros(B, dtype=np.uint8); mask[::3] = 1
+    env.step(np.full((B, 2), 3, dtype=np.int8))
+    out = env.reset(mask=mask)                         # masked, no goals: every env keeps its own
+    np.testing.assert_array_equal(_np(out["goal_idx"]), gi)
+    np.testing.assert_array_equal(env.unpack_state()["goal_bits"], gi[:, 0] | (gi[:, 1] << 1))
+    assert (env.unpack_state()["steps"][mask == 1] == 0).all() and (env.unpack_state()["steps"][mask == 0] == 1).all()
+
+
+def test_stage1_goal_redraw_on_in_kernel_reset():
+    """cfg.random_goal: every in-kernel episode reset draws the new goal from Philox keyed by
+    (seed; global env id, step) - the device form of train_offpolicy.py:291-296 - and the start
+    row follows the goal (checkers.py:271-276).  Checked against the CPU Philox twin, step by
+    step, and for balance."""
+    B, T, seed, off = 2048, 200, 77, 1 << 20
+    env = VecCheckers(B, random_goal=True, env_id_offset=off, **CK1)
+    g0 = np.random.default_rng(1).integers(0, 2, size=(B, 1)).astype(np.uint8)
+    env.reset(goal_idx=g0)
+    ro = env.rollout(T, seed=seed, t0=10, auto_reset=True, record_actions=True)
+    done, goal, vec = _np(ro["done"]), _np(ro["goal_idx"])[:, :, 0], _np(ro["vec"])[:, :, 0]
+    cur = g0[:, 0].copy()
+    n_new = 0
+    for t in range(T):
+        for b in np.nonzero(done[t])[0]:
+            ctr = np.array([(off + b) & 0xFFFFFFFF, (off + b) >> 32, (10 + t + 1) & 0xFFFFFFFF, 0x60A10000], dtype=np.uint32)
+            w = oracle.philox4x32_10(ctr, np.array([seed, 0], dtype=np.uint32))
+            cur[b] = w[0] >> 31
+            n_new += 1
+            assert vec[t, b, 0] == (2 if cur[b] else 0) + 2, "start row follows the goal"
+        np.testing.assert_array_equal(goal[t], cur, err_msg="t=%d" % t)
+    assert n_new > 5 * B
+    drawn = goal[1:][done[:-1] == 1]
+    assert abs(drawn.mean() - 0.5) < 0.02
+    # and the episodes are the reference's: replay every env on the oracle with the recorded actions
+    orc = oracle.OracleCheckers(B, **CK1)
+    orc.reset(g0)
+    acts = _np(ro["actions"])
+    cur = g0.copy()
+    for t in range(60):
+        ref = orc.step(acts[t])
+        np.testing.assert_array_equal(_np(ro["reward"][t]), ref["reward"].astype(np.float32))
+        np.testing.assert_array_equal(done[t], ref["done"])
+        if done[t].any():
+            cur[:, 0] = goal[t]
+            orc.reset(cur, mask=done[t])
+        np.testing.assert_array_equal(_np(ro["obs_self_t"][t]), orc.out["obs_self_t"].astype(np.float32))
+
+
+def test_random_goal_is_stage1_only():
+    from cm3_b200 import Cm3Error
+    with pytest.raises(Cm3Error):
+        VecCheckers(8, random_goal=True, **CK2)
+
+
+# ---------------------------------------------------------------------------------- collisions / reached
+def test_collision_count_and_reached_outputs_latch_the_finished_episode():
+    """`collisions` [T,B] is scenario.collisions after each step, BEFORE the in-kernel reset clears
+    it: at done steps it is the finished episode's total (train_onpolicy.py:356)."""
+    B, T = 512, 100
+    env = VecParticle(B, 2, MERGE, max_steps=presets.MAX_STEPS)
+    env.reset(seed=9)
+    st0 = env.get_state_host()
+    ro = env.rollout(T, seed=4, auto_reset=True, record_actions=True)
+    coll, reached, done, acts = (_np(ro[k]) for k in ("collisions", "reached", "done", "actions"))
+    po = oracle.OracleParticle(B, 2, max_steps=presets.MAX_STEPS)
+    po.set_state(pos=st0["sv"][:, :, 2:4].astype(np.float64), vel=st0["sv"][:, :, 0:2].astype(np.float64),
+                 landmarks=st0["landmarks"].astype(np.float64), steps=st0["steps"], collisions=st0["collisions"].astype(np.int64),
+                 reached=np.zeros((B, 2), dtype=np.uint8))
+    # first episode of every env against the oracle (float32 vs float64 agree on collision counts
+    # except at borderline distances: demand > 99.5 %)
+    alive = np.ones(B, dtype=bool)
+    agree = total = 0
+    for t in range(presets.MAX_STEPS):
+        po.step(acts[t])
+        c = po.get_state()["collisions"]
+        agree += int((coll[t][alive] == c[alive]).sum()); total += int(alive.sum())
+        alive &= done[t] == 0
+    assert agree / total > 0.995
+    # latch: monotone inside an episode, restarts after done
+    for t in range(1, T):
+        cont = done[t - 1] == 0
+        assert (coll[t][cont] >= coll[t - 1][cont]).all()
+    fresh = done[:-1] == 1
+    assert (coll[1:][fresh] <= 2).all()      # one step of a fresh 2-agent episode: 0 or 2
+    assert coll[:-1][fresh].max() > 2        # merge: finished episodes carry their collisions
+    # done <=> max_steps or everybody reached
+    assert ((reached == 3) <= (done == 1)).all()
+
+
+def test_explicit_and_in_kernel_reset_draws_are_different_streams():
+    """explicit reset k and the in-kernel reset at step k - 1 used to share a Philox counter."""
+    B = 256
+    env = VecParticle(B, 2, MERGE, max_steps=1)   # every step ends the episode
+    env.reset(seed=11, reset_counter=5)
+    explicit = env.state["sv"][:, :, 2:4].clone()
+    env.rollout(5, seed=11, t0=0, auto_reset=True)   # the reset after step 4 uses counter 5
+    auto = env.state["sv"][:, :, 2:4]
+    assert not torch.equal(explicit, auto)
+    assert (explicit - auto).abs().max() > 1e-3
+
+
+# ---------------------------------------------------------------------------------- host rollout, plans
+@pytest.mark.parametrize("tile", [None, torch.int8])
+def test_rollout_host_checkers_equals_device_steps(tile):
+    B, T = 640, 12
+    rng = np.random.default_rng(8)
+    acts = rng.integers(0, 5, size=(T, B, 2)).astype(np.int8)
+    a, b = VecCheckers(B, tile_dtype=tile, **CK2), VecCheckers(B, tile_dtype=tile, **CK2)
+    a.reset(goals=np.eye(2)); b.reset(goals=np.eye(2))
+    host = a.rollout_host(acts, auto_reset=True)
+    dev = b.rollout(T, actions=acts, auto_reset=True)
+    for f in gu.CHECKERS_FIELDS + ("goal_idx",):
+        np.testing.assert_array_equal(host[f], _np(dev[f]), err_msg=f)
+    if tile is torch.int8:
+        assert host["grid"].dtype == np.int8
+    # a second call continues the episodes
+    host = {k: v.copy() for k, v in a.rollout_host(acts, auto_reset=True, t0=T).items()}
+    dev = b.rollout(T, actions=acts, auto_reset=True, t0=T)
+    for f in gu.CHECKERS_FIELDS:
+        np.testing.assert_array_equal(host[f], _np(dev[f]), err_msg=f)
+
+
+def test_rollout_host_particle_equals_device_steps():
+    B, T = 1024, 10
+    rng = np.random.default_rng(8)
+    acts = rng.integers(0, 5, size=(T, B, 4)).astype(np.int8)
+    a, b = VecParticle(B, 4, ANTI, max_steps=6), VecParticle(B, 4, ANTI, max_steps=6)
+    a.reset(seed=1); b.reset(seed=1)
+    host = a.rollout_host(acts, seed=2, auto_reset=True)
+    dev = b.alloc_outputs(T)
+    for t in range(T):
+        b.rollout(1, actions=acts[t:t + 1], seed=2, t0=t, auto_reset=True, out={k: v[t:t + 1] for k, v in dev.items()})
+    for f in gu.PARTICLE_FIELDS + ("collisions", "reached"):
+        np.testing.assert_array_equal(host[f], _np(dev[f]), err_msg=f)
+
+
+@pytest.mark.parametrize("game", ["ck2", "pa4"])
+def test_planned_rollout_equals_rollout(game):
+    B, T = 2048, presets.MAX_STEPS
+    rng = np.random.default_rng(3)
+    if game == "ck2":
+        a, b = VecCheckers(B, **CK2), VecCheckers(B, **CK2)
+        a.reset(goals=np.eye(2)); b.reset(goals=np.eye(2))
+    else:
+        a, b = VecParticle(B, 4, ANTI, max_steps=T), VecParticle(B, 4, ANTI, max_steps=T)
+        a.reset(seed=1); b.reset(seed=1)
+    acts = torch.from_numpy(rng.integers(0, 5, size=(T, B, a.N)).astype(np.int8)).to(a.device)
+    plan = a.plan_rollout(T, actions=acts, auto_reset=True, seed=6)
+    for rep in range(2):
+        plan(rep * T)
+        want = b.rollout(T, actions=acts, auto_reset=True, seed=6, t0=rep * T)
+        torch.cuda.synchronize()
+        for f in want:
+            assert torch.equal(plan.out[f], want[f]), (rep, f)
+    short = a.plan_rollout(7, actions=acts[:7].contiguous(), auto_reset=True, seed=6, out={f: v[:7] for f, v in plan.out.items()})
+    short(2 * T)
+    want = b.rollout(7, actions=acts[:7], auto_reset=True, seed=6, t0=2 * T)
+    for f in want:
+        assert torch.equal(plan.out[f][:7], want[f]), f
+    with pytest.raises(ValueError):
+        a.plan_rollout(T, actions=acts.to(torch.int32))
