@@ -49,7 +49,7 @@ class ParticleConfig(C.Structure):
                 ("sensitivity", C.c_double), ("reach_thresh", C.c_double),
                 ("agents_x", C.c_double * MAX_AGENTS), ("agents_y", C.c_double * MAX_AGENTS),
                 ("landmarks_x", C.c_double * MAX_AGENTS), ("landmarks_y", C.c_double * MAX_AGENTS),
-                ("initial_std", C.c_double), ("prob_random", C.c_double)]
+                ("initial_std", C.c_double), ("prob_random", C.c_double), ("contact_cutoff", C.c_double)]
 
 
 class ParticleState(C.Structure):
@@ -68,6 +68,7 @@ SYMBOLS = {
     "cm3_abi_version": (C.c_int, []),
     "cm3_last_error": (C.c_char_p, []),
     "cm3_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cm3_stream_synchronize": (C.c_int, [_vp]),
     "cm3_checkers_create": (C.c_int, [C.POINTER(CheckersConfig), C.POINTER(_vp)]),
     "cm3_checkers_destroy": (C.c_int, [_vp]),
     "cm3_checkers_tiles": (C.c_int, [_vp, C.POINTER(_i32)]),

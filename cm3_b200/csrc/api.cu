@@ -1,11 +1,14 @@
 // api.cu - the extern "C" boundary declared in include/cm3env.h.
 // Handles hold configuration only; every buffer is the caller's (see the header).
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "params.cuh"
@@ -86,6 +89,54 @@ bool tma_enabled() {
         return !(v && v[0] == '0');
     }();
     return on;
+}
+
+bool balance_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_BALANCE");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
+int balance_waves(const void *kern, int threads, int smem, int nblocks) {
+    if (!balance_enabled()) return smem;
+    struct Entry { const void *kern; int dev, smem, nblocks, result; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return smem;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Entry &e : cache)
+            if (e.kern == kern && e.dev == dev && e.smem == smem && e.nblocks == nblocks) return e.result;
+    }
+    int result = smem;
+    int sms = 0, smem_sm = 0, optin = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) == cudaSuccess && per_sm > 0 && sms > 0) {
+        const long resident = (long)per_sm * sms;
+        if (nblocks > resident) {
+            const long waves = (nblocks + resident - 1) / resident;
+            const long last = nblocks - (waves - 1) * resident;
+            const int target = (int)((nblocks + waves * sms - 1) / (waves * sms));  // blocks per SM of equal waves
+            if (2 * last < resident && target < per_sm) {
+                // grow the request until the occupancy calculator agrees with the target
+                int lo = smem, hi = std::min(optin, smem_sm / target);
+                for (int s = hi; s >= lo; s -= 1024) {
+                    int got = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, threads, s) != cudaSuccess) break;
+                    if (got >= target) { if (got == target) result = s; break; }
+                }
+            }
+        }
+    }
+    (void)cudaGetLastError();
+    std::lock_guard<std::mutex> lk(mu);
+    cache.push_back(Entry{kern, dev, smem, nblocks, result});
+    return result;
 }
 
 static size_t real_size(int real) { return real == CM3_REAL_F64 ? 8 : 4; }
@@ -241,6 +292,11 @@ int cm3_device_count(int *count) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     *count = n;
+    return CM3_OK;
+}
+
+int cm3_stream_synchronize(void *stream) {
+    CM3_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return CM3_OK;
 }
 
@@ -533,6 +589,7 @@ void cm3_particle_default_config(cm3_particle_config *cfg, int32_t n_agents, int
     cfg->mass = 1.0;            /* core.py:47-51 */
     cfg->sensitivity = 5.0;     /* environment.py:211 */
     cfg->reach_thresh = 0.05;   /* multi-goal_spread.py:126 */
+    cfg->contact_cutoff = 1e-9; /* see the header */
 }
 
 int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
@@ -543,6 +600,7 @@ int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
         set_error("bad n_agents/num_envs/max_steps/real");
         return CM3_ERR_BAD_ARG;
     }
+    if (!(cfg->contact_cutoff >= 0.0)) { set_error("contact_cutoff must be >= 0"); return CM3_ERR_BAD_ARG; }
     if (cfg->n_agents > CM3_MAX_AGENTS) {
         set_error("n_agents=%d: the particle kernels keep 1..%d agents per env in registers", cfg->n_agents, CM3_MAX_AGENTS);
         return CM3_ERR_UNSUPPORTED;
@@ -573,7 +631,13 @@ int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {
     const bool sane = k > 0.0 && std::isfinite(k) && p.dist_min >= 0.0 && std::isfinite(p.dist_min) &&
                       std::isfinite(cfg->contact_force);
     const double inf = HUGE_VAL;
-    const double far2_f32 = sane ? std::pow((p.dist_min + 110.0 * k) * 1.02, 2) : inf;
+    double far_f32 = (p.dist_min + 110.0 * k) * 1.02;
+    // contact_cutoff: force <= contact_force * k * exp(x) < cutoff  <=>  dist > dist_min - k ln(cutoff / (contact_force k))
+    if (sane && cfg->contact_cutoff > 0.0 && cfg->contact_force > 0.0) {
+        const double lg = std::log(cfg->contact_cutoff / (cfg->contact_force * k));
+        if (lg < 0.0) far_f32 = std::min(far_f32, (p.dist_min - k * lg) * 1.0001);
+    }
+    const double far2_f32 = sane ? far_f32 * far_f32 : inf;
     const double far2_f64 = sane ? std::pow((p.dist_min + 760.0 * k) * 1.02, 2) : inf;
     const double near2 = (p.dist_min >= 0.0 && std::isfinite(p.dist_min)) ? std::pow(p.dist_min * 1.01, 2) + 1e-30 : inf;
     p.kd = PtConsts<double>{p.dt, 1.0 - p.damping, p.contact_force, p.contact_margin, p.dist_min, p.mass,

@@ -392,10 +392,15 @@ checkers_kernel(const __grid_constant__ CkParams p) {
             // ---- actions of all agents of my env
             int act[N];
             if (p.actions != nullptr) {
-                uint32_t w = act_word;  // picked up from the stream during the previous emit
-                if (!acts.on && live) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
+                if constexpr (N <= 4) {
+                    uint32_t w = act_word;  // picked up from the stream during the previous emit
+                    if (!acts.on && live) w = load_actions_packed<N>(p.actions + ((size_t)t * B + env) * N);
 #pragma unroll
-                for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
+                    for (int i = 0; i < N; ++i) act[i] = unpack_action(w, i);
+                } else {  // more than four agents do not fit the packed word: plain byte loads
+#pragma unroll
+                    for (int i = 0; i < N; ++i) act[i] = live ? (int)p.actions[((size_t)t * B + env) * N + i] : 0;
+                }
             } else {
                 // one Philox block of 4 words per 4 agents
 #pragma unroll
@@ -505,10 +510,12 @@ static int launch_ck(const Geo &geo, const CkParams &p, cudaStream_t stream) {
         set_error("board needs %d bytes of staging per block (limit %d)", smem, kCkDynSmemMax);
         return CM3_ERR_UNSUPPORTED;
     }
-    CM3_CUDA(ensure_smem_attr(kern, Geo::kStatic ? smem : kCkDynSmemMax, attr_done));
+    CM3_CUDA(ensure_smem_attr(kern, attr_done));
     const int ntiles = (p.B + Ly::EW - 1) / Ly::EW;
     const int nblocks = (ntiles + kCkWarpsPerBlock - 1) / kCkWarpsPerBlock;
-    CM3_CUDA(launch_kernel(kern, nblocks, kCkWarpsPerBlock * kWarp, smem, stream, pdl_enabled(), p));
+    // multi-step launches: equal waves (common.cuh: balance_waves)
+    const int smem_launch = (p.mode == kCkStep && p.T > 1) ? balance_waves((const void *)kern, kCkWarpsPerBlock * kWarp, smem, nblocks) : smem;
+    CM3_CUDA(launch_kernel(kern, nblocks, kCkWarpsPerBlock * kWarp, smem_launch, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 

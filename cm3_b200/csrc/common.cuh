@@ -317,19 +317,32 @@ struct TileTicket {
     }
 };
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): set once per pair, safely
-// from any number of host threads (one bit per device ordinal; ordinals >= 64 set it every time)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): raised to the device's
+// opt-in maximum once per pair, safely from any number of host threads (one bit per device ordinal;
+// ordinals >= 64 set it every time)
 template <typename K>
-inline cudaError_t ensure_smem_attr(K kern, int bytes, std::atomic<uint64_t> &done_mask) {
+inline cudaError_t ensure_smem_attr(K kern, std::atomic<uint64_t> &done_mask) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     const uint64_t bit = dev < 64 ? (1ull << dev) : 0ull;
     if (bit && (done_mask.load(std::memory_order_acquire) & bit)) return cudaSuccess;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e == cudaSuccess && bit) done_mask.fetch_or(bit, std::memory_order_release);
     return e;
 }
+
+// Wave balancing for multi-step launches (api.cu).  A T-step rollout keeps a block on its tile for
+// the whole launch, so a grid that needs a little more than w full waves of resident blocks ends
+// with a nearly empty wave running at a fraction of the machine (stage-1 Checkers at 65 536 envs:
+// 4096 tiles over 3404 slots - the last 692 blocks ran alone for a quarter of the launch).  Where the
+// last wave would be less than half full, the launch asks for enough EXTRA dynamic shared memory to
+// lower the blocks per SM to ceil(blocks / (waves * SMs)): the same number of waves, all of them
+// full.  Returns the dynamic shared-memory size to launch with (>= smem).
+int balance_waves(const void *kern, int threads, int smem, int nblocks);
 
 template <typename P>
 inline cudaError_t launch_kernel(void (*kern)(P), int nblocks, int nthreads, size_t smem, cudaStream_t stream,

@@ -249,8 +249,18 @@ template <> __device__ __forceinline__ void stage4<double>(unsigned char *tile, 
 // 20-40 % SLOWER at 65 536 envs: two warps per tile cap the kernel at 72 registers for a single
 // resident wave, and the physics warp lost more to spills and serialisation than the emitter took
 // off its chain.
+// Minimum resident blocks per SM asked of ptxas.  Left to itself it spends 118-128 registers on the
+// N = 3, 4 kernels; told to fit 24 / 20 blocks it needs 79 / 95 and still spills nothing.  At the
+// 65 536-env batch a fused rollout is one wave either way, but chained single-step launches overlap
+// only as far as blocks of two launches fit an SM together, and larger batches get deeper waves.
+#ifdef CM3_PT_MINB_OFF
+__host__ __device__ constexpr int pt_min_blocks(int) { return 1; }
+#else
+__host__ __device__ constexpr int pt_min_blocks(int N) { return N <= 3 ? 24 : N == 4 ? 20 : 1; }
+#endif
+
 template <int N, typename Real, bool GATHER, bool FULL>
-__global__ void __launch_bounds__(kWarp, 1) particle_kernel(const __grid_constant__ PtParams p) {
+__global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const __grid_constant__ PtParams p) {
     using Op = RealOps<Real>;
     using Gm = PtGeom<N, Real>;
     constexpr int NO = Gm::NO, LO = Gm::LO;
@@ -660,9 +670,11 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
     auto kern = particle_kernel<N, Real, GATHER, FULL>;
     constexpr int kSmem = Gm::kSmemBytes;
     static std::atomic<uint64_t> attr_done{0};
-    CM3_CUDA(ensure_smem_attr(kern, kSmem, attr_done));
+    CM3_CUDA(ensure_smem_attr(kern, attr_done));
     const int nblocks = (p.B + kWarp - 1) / kWarp;
-    CM3_CUDA(launch_kernel(kern, nblocks, kWarp, kSmem, stream, pdl_enabled(), p));
+    // multi-step launches: equal waves (common.cuh: balance_waves)
+    const int smem_launch = (p.mode == kPtStep && p.T > 1) ? balance_waves((const void *)kern, kWarp, kSmem, nblocks) : kSmem;
+    CM3_CUDA(launch_kernel(kern, nblocks, kWarp, smem_launch, stream, pdl_enabled(), p));
     return CM3_OK;
 }
 

@@ -59,8 +59,9 @@ class Checkers(object):
         """Returns (global_state, obs_others, obs_self_t, obs_self_v, total_reward, local_rewards,
         done), checkers.py:262."""
         a = np.asarray(actions).reshape(1, self.n_agents)
-        # host actions in, every field out in one packed copy (cm3_checkers_step_host_packed)
-        o = self._host(self._vec.step_host(a), self._OBS + ("reward", "local_rewards", "done"))
+        # one launch + one stream wait: the kernel reads the actions from and writes every field to
+        # pinned host memory directly (VecCheckers.step_mapped)
+        o = self._host(self._vec.step_mapped(a), self._OBS + ("reward", "local_rewards", "done"))
         local_rewards = [float(x) for x in o["local_rewards"]]
         return self._obs_tuple(o) + (np.float64(o["reward"]), local_rewards, bool(o["done"]))
 

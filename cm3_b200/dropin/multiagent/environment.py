@@ -69,6 +69,7 @@ class MultiAgentEnv(object):
                                 max_steps=max_steps, device=device, dtype=torch.float64, **overrides)
         self._results = None
         self._handed_out = None
+        self._fresh = False
         scenario._env = self
         self._upload_world()   # make_world() already drew an initial state (multi-goal_spread.py:62)
 
@@ -118,6 +119,7 @@ class MultiAgentEnv(object):
     def _world_was_reset(self):
         self._handed_out = None
         self._results = None
+        self._fresh = False
 
     def _ensure_synced(self):
         if self._stale():
@@ -147,6 +149,8 @@ class MultiAgentEnv(object):
     def _current_results(self):
         """Results for the scenario callbacks: the last launch's, or a fresh observe-only launch
         when the host state changed since."""
+        if self._fresh and self._results is not None:
+            return self._results
         if self._results is None or self._stale():
             keep = self._results
             self._upload_world()
@@ -163,15 +167,20 @@ class MultiAgentEnv(object):
         self._ensure_synced()
         a = np.array([[int(x) for x in action_n[:self.n]]], dtype=np.int64)
         self.steps += 1
-        # host actions in, every field (and the reached / collision flags) out in one packed copy
-        res = self._adopt(self._vec.step_host(a), with_reward=True)
+        # one launch + one stream wait: the kernel reads the actions from and writes every field (and
+        # the reached / collision flags) to pinned host memory directly (VecParticle.step_mapped)
+        res = self._adopt(self._vec.step_mapped(a), with_reward=True)
         obs_n, obs_others_n, reward_n, done_n = [], [], [], []
-        for agent in self.agents:   # callback order of environment.py:95-104
-            obs_self, obs_others = self._get_obs(agent)
-            obs_n.append(obs_self)
-            obs_others_n.append(obs_others)
-            reward_n.append(self._get_reward(agent))
-            done_n.append(self._get_done(agent))
+        self._fresh = True          # nothing can have touched the entities since _adopt: the
+        try:                        # callbacks below skip the staleness check
+            for agent in self.agents:   # callback order of environment.py:95-104
+                obs_self, obs_others = self._get_obs(agent)
+                obs_n.append(obs_self)
+                obs_others_n.append(obs_others)
+                reward_n.append(self._get_reward(agent))
+                done_n.append(self._get_done(agent))
+        finally:
+            self._fresh = False
         reward = np.float64(res["reward"])   # np.sum(reward_n), evaluated on the device in index order
         global_state = res["global_state"].copy()
         done = bool(res["done"])

@@ -59,6 +59,12 @@ int cm3_abi_version(void);
 const char *cm3_last_error(void);
 /* number of visible CUDA devices (0 when the driver is absent) */
 int cm3_device_count(int *count);
+/* waits for the work enqueued on `stream` (cudaStreamSynchronize): for bindings without a CUDA
+ * runtime of their own.  Together with pinned host memory - which the device addresses directly
+ * under unified addressing - this is the low-latency B = 1 path: pass pinned host pointers as
+ * `actions` and `outs` of cm3_*_step and call cm3_stream_synchronize; the kernel reads the actions
+ * from and writes the outputs to host memory itself, with no copy calls on the host path. */
+int cm3_stream_synchronize(void *stream);
 
 /* ------------------------------------------------------------------ Checkers */
 
@@ -256,6 +262,15 @@ typedef struct {
     double landmarks_x[CM3_MAX_AGENTS], landmarks_y[CM3_MAX_AGENTS];
     double initial_std;
     double prob_random;
+    /* float kernels only: an agent pair whose contact force is provably smaller than this (in force
+     * units; the action force is `sensitivity` = 5) is not evaluated.  The reference evaluates the
+     * softplus penetration for every pair at every distance (core.py:143-155); its tail decays as
+     * contact_force * contact_margin * exp(-(dist - dist_min) / contact_margin), i.e. below 1e-9
+     * beyond dist_min + 18.4 contact_margin - four orders of magnitude under float32 resolution of
+     * the quantities it is added to.  Default 1e-9 (cm3_particle_default_config); 0 = skip a pair
+     * only where its force is exactly zero in float arithmetic (round 1's criterion).  The double
+     * kernels always use the exact-zero criterion. */
+    double contact_cutoff;
 } cm3_particle_config;
 
 void cm3_particle_default_config(cm3_particle_config *cfg, int32_t n_agents, int32_t max_steps);

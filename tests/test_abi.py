@@ -40,7 +40,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.CheckersConfig) == 5 * 4 + 2 * 32 + 4 * 4 + 4 + 8 + 8  # padded to 8
     assert C.sizeof(L.CheckersState) == 32
     assert C.sizeof(L.CheckersOutputs) == 72
-    assert C.sizeof(L.ParticleConfig) == 6 * 4 + 8 + 8 * 8 + 4 * 64 + 16
+    assert C.sizeof(L.ParticleConfig) == 6 * 4 + 8 + 8 * 8 + 4 * 64 + 24
     assert C.sizeof(L.ParticleState) == 48
     assert C.sizeof(L.ParticleOutputs) == 64
 
