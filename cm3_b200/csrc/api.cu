@@ -75,6 +75,15 @@ bool full_enabled() {
     return on;
 }
 
+int chain_parts(int ntiles) {
+    static const int forced = [] {
+        const char *v = getenv("CM3_CHAIN_PARTS");
+        return v ? atoi(v) : 0;
+    }();
+    const int parts = forced > 0 ? forced : 2;
+    return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
+}
+
 bool dyn_geometry_forced() {
     static const bool on = [] {
         const char *v = getenv("CM3_CK_DYNAMIC");

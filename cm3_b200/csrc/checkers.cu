@@ -167,7 +167,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     const uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * kCkWarpsPerBlock + warp;
+    const int tile = p.tile0 + blockIdx.x * kCkWarpsPerBlock + warp;
     // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
     TileTicket ticket;
     ticket.take(tile * EW < p.B ? p.sync : nullptr, tile, lane);
@@ -515,7 +515,13 @@ static int launch_ck(const Geo &geo, const CkParams &p, cudaStream_t stream) {
     const int nblocks = (ntiles + kCkWarpsPerBlock - 1) / kCkWarpsPerBlock;
     // multi-step launches: equal waves (common.cuh: balance_waves)
     const int smem_launch = (p.mode == kCkStep && p.T > 1) ? balance_waves((const void *)kern, kCkWarpsPerBlock * kWarp, smem, nblocks) : smem;
-    CM3_CUDA(launch_kernel(kern, nblocks, kCkWarpsPerBlock * kWarp, smem_launch, stream, pdl_enabled(), p));
+    const int parts = (p.chained && kCkWarpsPerBlock == 1) ? chain_parts(ntiles) : 1;
+    for (int i = 0; i < parts; ++i) {  // disjoint tile ranges; one grid unless chained (params.cuh: chain_parts)
+        CkParams q = p;
+        q.tile0 = (int)((long long)nblocks * i / parts);
+        const int n = (int)((long long)nblocks * (i + 1) / parts) - q.tile0;
+        if (n > 0) CM3_CUDA(launch_kernel(kern, n, kCkWarpsPerBlock * kWarp, smem_launch, stream, pdl_enabled(), q));
+    }
     return CM3_OK;
 }
 

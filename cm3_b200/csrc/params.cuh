@@ -45,6 +45,7 @@ struct CkParams {
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
     int chained;      // 1: wait for this tile's predecessor only (TileTicket) instead of griddepcontrol.wait
+    int tile0;        // first tile of this launch (a chained step is issued as several partial grids)
     int random_goal;  // N == 1: in-kernel resets redraw the goal (train_offpolicy.py:291-296)
     int R, C, O;      // board geometry for the kernels that take it as data (checkers.cu: DynGeo)
     unsigned long long color_mask[2];  // bitboard of the green / orange cells (checkers.py:54-63)
@@ -79,7 +80,7 @@ struct PtParams {
     int n_dst;
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
-    int chained;  // see CkParams
+    int chained, tile0;  // see CkParams
     unsigned long long seed;
     long long t0, env_id_offset, reset_counter;
     double dt, damping, contact_force, contact_margin, dist_min, mass, sensitivity, reach_thresh;
@@ -104,5 +105,10 @@ int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);
 bool full_enabled();  // particle kernel: the specialised all-outputs / whole-tiles instantiation (CM3_PT_FULL=0 disables)
 bool tma_enabled();  // swizzled tiles + tensor-map stores in the particle kernel (CM3_TMA=0 disables)
 bool pdl_enabled();  // programmatic dependent launch between consecutive step launches (CM3_PDL=0 disables)
+// Partial grids of a chained single-step launch.  All blocks of one particle launch are resident at
+// once and in the same phase (compute, then store), and blocks of the next launch only get the slots
+// the previous ones free: issued as `parts` grids over disjoint tile ranges, the stores of one part
+// overlap the compute of the next (CM3_CHAIN_PARTS overrides the default).
+int chain_parts(int ntiles);
 
 }  // namespace cm3

@@ -249,15 +249,15 @@ template <> __device__ __forceinline__ void stage4<double>(unsigned char *tile, 
 // 20-40 % SLOWER at 65 536 envs: two warps per tile cap the kernel at 72 registers for a single
 // resident wave, and the physics warp lost more to spills and serialisation than the emitter took
 // off its chain.
-// Minimum resident blocks per SM asked of ptxas.  Left to itself it spends 118-128 registers on the
-// N = 3, 4 kernels; told to fit 24 / 20 blocks it needs 79 / 95 and still spills nothing.  At the
-// 65 536-env batch a fused rollout is one wave either way, but chained single-step launches overlap
-// only as far as blocks of two launches fit an SM together, and larger batches get deeper waves.
-#ifdef CM3_PT_MINB_OFF
-__host__ __device__ constexpr int pt_min_blocks(int) { return 1; }
-#else
-__host__ __device__ constexpr int pt_min_blocks(int N) { return N <= 3 ? 24 : N == 4 ? 20 : 1; }
+// Measured and dropped (round 2, profiles/r02b_ab.txt): asking ptxas for 20 / 24 resident blocks per
+// SM (95 / 79 registers instead of 128 / 118, no spills) so that blocks of two chained single-step
+// launches fit an SM together.  The shorter register budget lengthens the dependent chains:
+// fused PA4 0.92 -> 0.77, PA3 0.87 -> 0.61, and even the chained per-step launches lost (0.78 -> 0.74).
+// CM3_PT_MINB=<n> rebuilds that variant.
+#ifndef CM3_PT_MINB
+#define CM3_PT_MINB 1
 #endif
+__host__ __device__ constexpr int pt_min_blocks(int) { return CM3_PT_MINB; }
 
 template <int N, typename Real, bool GATHER, bool FULL>
 __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const __grid_constant__ PtParams p) {
@@ -269,14 +269,15 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
     const int lane = threadIdx.x;
     // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
     TileTicket ticket;
-    ticket.take(p.sync, blockIdx.x, lane);
+    const int tile = p.tile0 + (int)blockIdx.x;
+    ticket.take(p.sync, tile, lane);
     if (ticket.mine != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *stage_base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
     const bool reset_mode = !FULL && p.mode == kPtReset;
-    const int env0 = blockIdx.x * kWarp;
+    const int env0 = tile * kWarp;
     const int env = env0 + lane;
     const int nenv = FULL ? kWarp : min(kWarp, p.B - env0);
     const bool valid = FULL || lane < nenv;
@@ -674,7 +675,13 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
     const int nblocks = (p.B + kWarp - 1) / kWarp;
     // multi-step launches: equal waves (common.cuh: balance_waves)
     const int smem_launch = (p.mode == kPtStep && p.T > 1) ? balance_waves((const void *)kern, kWarp, kSmem, nblocks) : kSmem;
-    CM3_CUDA(launch_kernel(kern, nblocks, kWarp, smem_launch, stream, pdl_enabled(), p));
+    const int parts = p.chained ? chain_parts(nblocks) : 1;
+    for (int i = 0; i < parts; ++i) {  // disjoint tile ranges; one grid unless chained (params.cuh: chain_parts)
+        PtParams q = p;
+        q.tile0 = (int)((long long)nblocks * i / parts);
+        const int n = (int)((long long)nblocks * (i + 1) / parts) - q.tile0;
+        if (n > 0) CM3_CUDA(launch_kernel(kern, n, kWarp, smem_launch, stream, pdl_enabled(), q));
+    }
     return CM3_OK;
 }
 

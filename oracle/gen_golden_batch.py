@@ -116,10 +116,9 @@ def checkers_batch(ck, alg_mod, rb_mod):
         fix["in_" + k] = np.stack([r[j] for r in raw])
     fix["ring_capacity"] = np.array(50)
     # which added transition sits in each ring slot (derived from the reference's memory itself)
-    fix["ring_slot_source"] = np.array([next(i for i in range(len(raw) - 1, -1, -1)
-                                             if np.array_equal(raw[i][1], memory[s][1]) and np.array_equal(raw[i][6], memory[s][6])
-                                             and np.array_equal(raw[i][0], memory[s][0]) and raw[i][7] == memory[s][7])
-                                        for s in range(50)])
+    def same(i, s):   # every one of the 16 fields
+        return all(np.array_equal(np.asarray(raw[i][j], dtype=np.float64), np.asarray(memory[s][j], dtype=np.float64)) for j in range(16))
+    fix["ring_slot_source"] = np.array([next(i for i in range(len(raw) - 1, -1, -1) if same(i, s)) for s in range(50)])
     return fix
 
 
@@ -133,6 +132,7 @@ def particle_batch(MultiAgentEnv, scenarios, alg_mod):
     env = MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation, None, scenario.done, max_steps=33)
     l_action, l_goal = 5, 2
     rows, raw, coll = [], [], []
+    bench_rows, bench_pos, bench_lm = [], [], []
     for ep in range(2):
         global_state, local_others, local_self, done = env.reset()        # train_onpolicy.py:282
         goals = np.zeros([n, l_goal])
@@ -145,6 +145,10 @@ def particle_batch(MultiAgentEnv, scenarios, alg_mod):
                       next_global_state, np.array(next_local_others), np.array(next_local_self), done, goals]   # :336
             rows.append(transition(fields))
             raw.append([np.array(f, dtype=np.float64) if not isinstance(f, (bool, np.bool_)) else np.array(f) for f in fields])
+            # the info callback the trainers never wire (multi-goal_spread.py:95-111), on the same states
+            bench_rows.append(np.array([scenario.benchmark_data(a, env.world) for a in env.world.agents], dtype=np.float64))
+            bench_pos.append(np.array([a.state.p_pos for a in env.world.agents]))
+            bench_lm.append(np.array([l.state.p_pos for l in env.world.landmarks]))
             global_state, local_others, local_self = next_global_state, next_local_others, next_local_self
         coll.append(scenario.collisions)                                  # :356 reads this per episode
     batch = np.array(rows)
@@ -158,6 +162,8 @@ def particle_batch(MultiAgentEnv, scenarios, alg_mod):
     for j, k in enumerate(in_names):
         fix["in_" + k] = np.stack([r[j] for r in raw])
     fix["episode_collisions"] = np.array(coll)
+    fix["benchmark_data"] = np.stack(bench_rows)      # [T, N, 4] = (rew, collisions, min_dists, occupied_landmarks)
+    fix["benchmark_pos"], fix["benchmark_landmarks"] = np.stack(bench_pos), np.stack(bench_lm)
     return fix
 
 

@@ -36,32 +36,40 @@ def main():
     report = {}
     for kind in ("ck2", "pm2"):
         shard = EnvShard(total)
-        ref = None
+        refs = None
         if rank == 0:
             full = make(kind, total, shard.device, 0)
-            ref = full.rollout(T, actions=None, seed=seed, auto_reset=True)
+            refs = [{k: v.clone() for k, v in full.rollout(T, actions=None, seed=seed, t0=r * T, auto_reset=True).items()}
+                    for r in range(2)]
             torch.cuda.synchronize()
-        for mode in ("nccl", "peer"):
+        # peer_db: two symmetric buffers, rollout k + 1 enqueued while the stores of rollout k are published
+        for mode in ("nccl", "peer", "peer_db"):
             env = make(kind, shard.count, shard.device, shard.start)
             try:
-                g = RolloutAllGather(env, T, shard=shard, mode=mode)
+                g = RolloutAllGather(env, T, shard=shard, mode=mode.split("_")[0], double_buffer=mode.endswith("_db"))
             except Exception as e:  # noqa: BLE001
                 report["%s_%s" % (kind, mode)] = "unavailable: %r" % (e,)
                 if mode == "nccl":
                     raise
                 continue
-            out = g.rollout(seed=seed, auto_reset=True)
+            outs = []
+            for r in range(2):
+                o = g.rollout(seed=seed, t0=r * T, auto_reset=True, wait=False)
+                outs.append(o if mode.endswith("_db") else {k: v.clone() for k, v in o.items()})
+            for o in outs:
+                g.wait_ready(o) if mode.endswith("_db") else None
             torch.cuda.synchronize()
             dist.barrier()
             ok = True
             if rank == 0:
-                for k, v in ref.items():
-                    same = torch.equal(out[k].reshape(v.shape), v)
-                    ok = ok and same
-                    if not same:
-                        report["%s_%s_mismatch" % (kind, mode)] = k
+                for r in range(2):
+                    for k, v in refs[r].items():
+                        same = torch.equal(outs[r][k].reshape(v.shape), v)
+                        ok = ok and same
+                        if not same:
+                            report["%s_%s_mismatch" % (kind, mode)] = "%s (rollout %d)" % (k, r)
             # every rank must hold the same gathered batch
-            chk = torch.stack([out[k].double().sum() for k in sorted(out)])
+            chk = torch.stack([o[k].double().sum() for o in outs for k in sorted(o)])
             lst = [torch.empty_like(chk) for _ in range(world)]
             dist.all_gather(lst, chk)
             same_everywhere = all(torch.equal(lst[0], x) for x in lst)

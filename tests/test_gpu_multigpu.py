@@ -29,5 +29,5 @@ def test_sharded_rollout_all_gather_is_shard_invariant():
     rep = json.loads(line[len("MULTIGPU_REPORT "):])
     print(rep)
     assert rep["ck2_nccl"] == "ok" and rep["pm2_nccl"] == "ok", rep
-    for k in ("ck2_peer", "pm2_peer"):
+    for k in ("ck2_peer", "pm2_peer", "ck2_peer_db", "pm2_peer_db"):
         assert rep[k] == "ok" or rep[k].startswith("unavailable"), rep

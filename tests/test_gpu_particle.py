@@ -117,12 +117,24 @@ def test_oracle_teacher_forced_f32_large(N, preset, B):
         out = np_of(env.step(a))
         for f in ("global_state", "obs_others", "obs_self", "reward", "reward_n"):
             np.testing.assert_allclose(out[f], ref[f], rtol=F32_RTOL, atol=F32_ATOL, err_msg="t=%d %s" % (t, f))
-        # done / collisions can legitimately flip only when a distance sits within float32
-        # rounding of a threshold; require agreement wherever the oracle is not borderline
+        # done and the collision counter can legitimately differ from the float64 oracle only where a
+        # distance sits within float32 rounding of its threshold: the reach test |pos - landmark| vs
+        # 0.05 (multi-goal_spread.py:126) or a pair distance vs dist_min = 0.3 (:117).  Everywhere
+        # else - computed from the oracle's own float64 state - they must be EQUAL.
         st2 = orc.get_state()
         n_contacts += int((st2["collisions"] - st["collisions"]).sum())
-        agree = (out["done"] == ref["done"]).mean()
-        assert agree > 0.999, agree
+        eps = 4e-6
+        to_goal = np.sqrt(((st2["pos"] - st2["landmarks"]) ** 2).sum(-1))               # [B, N]
+        border = (np.abs(to_goal - 0.05) < eps).any(axis=1)
+        border_c = np.zeros(B, dtype=bool)
+        for i in range(N):
+            for j in range(i + 1, N):
+                gap = np.sqrt(((st2["pos"][:, i] - st2["pos"][:, j]) ** 2).sum(-1))
+                border_c |= np.abs(gap - 0.3) < eps
+        np.testing.assert_array_equal(out["done"][~border], ref["done"][~border], err_msg="t=%d done" % t)
+        got_c = env.state["collisions"].cpu().numpy()
+        np.testing.assert_array_equal(got_c[~border_c], st2["collisions"][~border_c], err_msg="t=%d collisions" % t)
+        assert border.mean() < 5e-3 and border_c.mean() < 5e-3
     assert N == 1 or n_contacts > 0
 
 
@@ -378,3 +390,39 @@ def test_coincident_agents_propagate_nan_like_the_reference(dtype, rtol, atol):
     np.testing.assert_array_equal(env.state["collisions"].cpu().numpy(), orc.get_state()["collisions"])
     # the pair at 0.29 was pushed apart by the literal contact force (new distance 0.6 - 0.29 +- actions)
     assert abs(ref["global_state"][1, 2, 2] - ref["global_state"][1, 3, 2]) > 0.29
+
+
+def test_float32_free_running_drift_through_contacts_is_bounded_and_recorded():
+    """DESIGN section 7 states that free-running float32 trajectories stay ~1e-6 from the float64
+    reference while no contact occurs and drift to ~1e-3 through contacts (the contact is stiff: gain
+    100, margin 1e-3).  This measures it: 4096 antipodal envs (N = 4) under a goal-seeking
+    policy - every episode crosses the centre - run free for one episode on the float32 kernel and on
+    the float64 oracle from the same start and the same actions.  The quantiles are asserted (and
+    printed: `pytest -s`), so the prose has a test behind it."""
+    B, N, T = 4096, 4, presets.MAX_STEPS
+    cfg = presets.PARTICLE["antipodal"]
+    rng = np.random.default_rng(11)
+    pos = np.tile(np.stack([cfg["agents_x"], cfg["agents_y"]], axis=1), (B, 1, 1)) + rng.normal(0, 0.02, (B, N, 2))
+    pos = pos.astype(np.float32).astype(np.float64)
+    lm = np.tile(np.stack([cfg["landmarks_x"], cfg["landmarks_y"]], axis=1), (B, 1, 1)).astype(np.float64)
+    orc = oracle.OracleParticle(B, N, max_steps=T + 1, nthreads=oracle.max_threads())
+    env = VecParticle(B, N, cfg, max_steps=T + 1)
+    orc.reset_to(pos, lm)
+    env.reset(init_pos=pos, init_landmarks=lm)
+    err = np.zeros((T, B))
+    touched = np.zeros(B, dtype=bool)
+    for t in range(T):
+        a = seek_actions(orc.get_state()["pos"], lm, rng)      # the oracle's trajectory decides the actions
+        ref = orc.step(a)
+        out = env.step(a)["global_state"].cpu().numpy()
+        err[t] = np.abs(out - ref["global_state"]).reshape(B, -1).max(axis=1)
+        touched |= orc.get_state()["collisions"] > 0
+    final = err[-1]
+    free, hit = final[~touched], final[touched]
+    stats = dict(envs_with_contact=int(touched.sum()), free_max=float(free.max()) if free.size else 0.0,
+                 hit_median=float(np.median(hit)), hit_p99=float(np.quantile(hit, 0.99)), hit_max=float(hit.max()))
+    print("float32 free-running drift after %d steps: %s" % (T, stats))
+    assert touched.mean() > 0.3                      # the policy does drive agents through each other
+    assert stats["free_max"] < 2e-5                  # contact-free episodes: float32 rounding only
+    assert stats["hit_median"] < 1e-3 and stats["hit_p99"] < 0.2
+    assert np.isfinite(err).all()
