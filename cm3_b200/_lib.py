@@ -11,7 +11,7 @@ REAL_F32, REAL_F64 = 0, 1
 TILE_REAL, TILE_I8 = 0, 1
 
 STATUS_NAMES = {0: "CM3_OK", -1: "CM3_ERR_BAD_ARG", -2: "CM3_ERR_BAD_SHAPE", -3: "CM3_ERR_CUDA",
-                -4: "CM3_ERR_UNSUPPORTED", -5: "CM3_ERR_NO_DEVICE"}
+                -4: "CM3_ERR_UNSUPPORTED", -5: "CM3_ERR_NO_DEVICE", -6: "CM3_ERR_NCCL"}
 
 
 class Cm3Error(RuntimeError):
@@ -118,6 +118,10 @@ SYMBOLS = {
     "cm3_particle_set_state": (C.c_int, [_vp, C.POINTER(ParticleState), C.POINTER(ParticleState), _vp]),
     "cm3_particle_step_host_packed": (C.c_int, [_vp, C.POINTER(ParticleState), _vp, _vp,
                                                 C.POINTER(ParticleOutputs), _vp, _vp, C.c_size_t, _vp]),
+    "cm3_comm_unique_id": (C.c_int, [_vp]),
+    "cm3_comm_init": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "cm3_comm_allgather": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "cm3_comm_destroy": (C.c_int, [_vp]),
 }
 
 _lib = None

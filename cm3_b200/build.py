@@ -7,11 +7,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # (source, extra defines, object suffix): checkers.cu is compiled once per arithmetic type so the
 # two halves of its template instantiations build in parallel
-UNITS = [("api.cu", (), "api"), ("particle.cu", (), "particle"),
+UNITS = [("api.cu", (), "api"), ("comm.cu", (), "comm"), ("particle.cu", (), "particle"),
          ("checkers.cu", ("CM3_CK_REAL=0",), "checkers_f32"),
          ("checkers.cu", ("CM3_CK_REAL=1",), "checkers_f64"),
          ("checkers.cu", ("CM3_CK_REAL=2",), "checkers_f32_i8")]
-SOURCES = ["api.cu", "checkers.cu", "particle.cu"]
+SOURCES = ["api.cu", "comm.cu", "checkers.cu", "particle.cu"]
 HEADERS = ["common.cuh", "params.cuh", os.path.join("..", "..", "include", "cm3env.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -58,5 +58,5 @@ def build_library(force=False, verbose=False, defines=(), output=None):
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.check_call([_nvcc()] + ARCH_FLAGS + ["-shared", "-o", out] + objs)
+    subprocess.check_call([_nvcc()] + ARCH_FLAGS + ["-shared", "-o", out] + objs + ["-ldl"])
     return out

@@ -80,7 +80,7 @@ int chain_parts(int ntiles) {
         const char *v = getenv("CM3_CHAIN_PARTS");
         return v ? atoi(v) : 0;
     }();
-    const int parts = forced > 0 ? forced : 2;
+    const int parts = forced > 0 ? forced : 1;  // measured: 2, 3, 4 parts are all slower (profiles/r02c_ab.txt)
     return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
 }
 
@@ -598,7 +598,7 @@ void cm3_particle_default_config(cm3_particle_config *cfg, int32_t n_agents, int
     cfg->mass = 1.0;            /* core.py:47-51 */
     cfg->sensitivity = 5.0;     /* environment.py:211 */
     cfg->reach_thresh = 0.05;   /* multi-goal_spread.py:126 */
-    cfg->contact_cutoff = 1e-9; /* see the header */
+    cfg->contact_cutoff = 0.0;  /* exact-zero criterion; see the header */
 }
 
 int cm3_particle_create(const cm3_particle_config *cfg, cm3_particle_t *out) {

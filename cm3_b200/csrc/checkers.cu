@@ -167,6 +167,9 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     const uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the one thread that issues, commits and waits for this warp's bulk stores (elect.sync: ptxas then
+    // knows a single thread is active and needs no operand loop around the TMA instructions)
+    const bool leader = elect_one();
     const int tile = p.tile0 + blockIdx.x * kCkWarpsPerBlock + warp;
     // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
     TileTicket ticket;
@@ -245,7 +248,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         const uint32_t act_loaded = acts.on ? acts.load(t + 1) : 0u;
         if (acts.on) acts.prefetch(t + 3);
         if (pending) {
-            if (lane < 2) bulk_wait_read();
+            if (leader) bulk_wait_read();
         }
         __syncwarp();
         // ---------------- window of agent a (get_obs, checkers.py:97-109)
@@ -292,16 +295,16 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 Tile *g = reinterpret_cast<Tile *>(p.out[d].obs_self_t) + (slot + env0) * (size_t)(N * WW3);
                 if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
 #ifdef CM3_L2_HINT_BULK
-                    if (lane == 0) bulk_store_hint(g, stage_win, bytes, l2_policy_evict_first());
+                    if (leader) bulk_store_hint(g, stage_win, bytes, l2_policy_evict_first());
 #else
-                    if (lane == 0) bulk_store(g, stage_win, bytes);
+                    if (leader) bulk_store(g, stage_win, bytes);
 #endif
                     pending = true;
                 } else {
                     for (int idx = lane; idx < nenv * N * WW3; idx += kWarp) g[idx] = stage_win[idx];
                 }
             }
-            if (lane == 0) bulk_commit();
+            if (leader) bulk_commit();
         }
         // ---------------- global grid (get_valid_grid, :66-76).  N > 1: lane a < 2 writes channel a;
         // N == 1: the env's second lane writes both channels
@@ -335,16 +338,16 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 Tile *g = reinterpret_cast<Tile *>(p.out[d].grid) + (slot + env0) * (size_t)G;
                 if (nenv == EW && ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0) {
 #ifdef CM3_L2_HINT_BULK
-                    if (lane == 1) bulk_store_hint(g, stage_grid, bytes, l2_policy_evict_first());
+                    if (leader) bulk_store_hint(g, stage_grid, bytes, l2_policy_evict_first());
 #else
-                    if (lane == 1) bulk_store(g, stage_grid, bytes);
+                    if (leader) bulk_store(g, stage_grid, bytes);
 #endif
                     pending = true;
                 } else {
                     for (int idx = lane; idx < nenv * G; idx += kWarp) g[idx] = stage_grid[idx];
                 }
             }
-            if (lane == 1) bulk_commit();
+            if (leader) bulk_commit();
         }
         if (acts.on) act_word = acts.hand_over(t, act_loaded, e);
         // ---------------- small per-agent vectors, straight from registers
@@ -493,7 +496,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     }
     ticket.publish(lane);  // this tile's next launch may go ahead
     // smem must outlive the async reads; the global writes themselves complete with the grid
-    if (pending && lane < 2) bulk_wait_read();
+    if (pending && leader) bulk_wait_read();
 }
 
 // ------------------------------------------------------------------------ host side

@@ -103,6 +103,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return pol;
 }
 
+// one thread of the (fully active) warp, in a form ptxas understands as "exactly one thread": the
+// uniform-register operands of a TMA instruction issued under this predicate need no waterfall loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---------------------------------------------------------------- action stream

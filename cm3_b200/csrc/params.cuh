@@ -105,10 +105,12 @@ int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);
 bool full_enabled();  // particle kernel: the specialised all-outputs / whole-tiles instantiation (CM3_PT_FULL=0 disables)
 bool tma_enabled();  // swizzled tiles + tensor-map stores in the particle kernel (CM3_TMA=0 disables)
 bool pdl_enabled();  // programmatic dependent launch between consecutive step launches (CM3_PDL=0 disables)
-// Partial grids of a chained single-step launch.  All blocks of one particle launch are resident at
-// once and in the same phase (compute, then store), and blocks of the next launch only get the slots
-// the previous ones free: issued as `parts` grids over disjoint tile ranges, the stores of one part
-// overlap the compute of the next (CM3_CHAIN_PARTS overrides the default).
+// Partial grids of a chained single-step launch (experiment, default 1 = off).  All blocks of one
+// particle launch are resident at once and in the same phase (compute, then store), and blocks of
+// the next launch only get the slots the previous ones free; the idea was that `parts` grids over
+// disjoint tile ranges would let the stores of one part overlap the compute of the next.  Measured
+// slower for every workload at 2, 3 and 4 parts (profiles/r02c_ab.txt: the extra launches cost more
+// than the overlap returns); CM3_CHAIN_PARTS=<n> re-enables it.
 int chain_parts(int ntiles);
 
 }  // namespace cm3

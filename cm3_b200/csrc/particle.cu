@@ -234,6 +234,16 @@ template <> __device__ __forceinline__ void stage4<double>(unsigned char *tile, 
     *reinterpret_cast<double2 *>(tile + (o1 ^ ((o1 >> 3) & mask))) = make_double2(c, d);
 }
 
+// Measured and dropped (round 2, profiles/r02d_ab.txt): float kernels with at most two agents storing
+// their observation records straight from registers (16-byte streaming stores, no staging, no TMA, no
+// drain wait - see emit).  The records of a warp are contiguous, but every store instruction fills
+// only half of each 32-byte sector it touches: PM2 fused 0.63 -> 0.42 at 65 536 envs, 0.91 -> 0.60 at
+// 262 144.  Full-line TMA stores it is.  CM3_PT_DIRECT=1 rebuilds the variant.
+#ifndef CM3_PT_DIRECT
+#define CM3_PT_DIRECT 0
+#endif
+template <int N> constexpr bool kDirectStores = (CM3_PT_DIRECT != 0) && N <= 2;
+
 // GATHER = false: one destination set (reset / step / rollout); GATHER = true: rollout_gather,
 // every element goes to n_dst destination sets (peer GPUs), linear tiles + plain bulk stores.
 //
@@ -267,6 +277,11 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
     constexpr uint32_t RS = (uint32_t)sizeof(Real);
 
     const int lane = threadIdx.x;
+    // The thread that issues, commits and waits for this warp's TMA stores.  Elected with elect.sync
+    // rather than picked as "lane 0": under an `if (lane == 0)` ptxas cannot see that a single thread
+    // is active and wraps every TMA instruction in a loop that moves its (uniform-register) operands
+    // over one distinct value at a time - ~15 instructions per store, three stores per step.
+    const bool leader = elect_one();
     // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
     TileTicket ticket;
     const int tile = p.tile0 + (int)blockIdx.x;
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
     const bool has_rn = FULL || o0.reward_n != nullptr, has_rw = FULL || o0.reward != nullptr, has_dn = FULL || o0.done != nullptr;
     const bool tma = FULL || (!GATHER && p.tma != 0);           // swizzled tiles + tensor-map stores
     const uint32_t mask_row = tma ? Gm::kRowMask : 0u, mask_oo = tma ? Gm::kOthMask : 0u;
-    if (tma && threadIdx.x == 0) {
+    if (tma && leader) {
         if (has_oo) tma_prefetch_map(&p.tm.oo);
         if (has_gs) tma_prefetch_map(&p.tm.gs);
         if (has_os) tma_prefetch_map(&p.tm.os);
@@ -365,11 +380,34 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
         // next step's action word: in flight from here to the end of this phase (ActionStream)
         const uint32_t act_loaded = acts.on ? acts.load(t + 1) : 0u;
         if (acts.on) acts.prefetch(t + 3);
+        if constexpr (FULL && kDirectStores<N> && sizeof(Real) == 4) {
+            // N <= 2: an env's record is 16 N / 16 N max(N-1,1) bytes, consecutive lanes write
+            // consecutive records, so the tile is a contiguous 512 N bytes per field either way.  Plain
+            // 16-byte streaming stores from registers (two per field and lane for N = 2) reach the same
+            // lines without the staging stores, the proxy fence, the three TMA issues and - the point -
+            // without ever waiting for a staging tile to drain: with these small records a step is
+            // short compared with the drain, and the wait was most of the step.
+            const size_t rec = (size_t)t * OB + oe0 + env;
+            float4 *gs = reinterpret_cast<float4 *>(reinterpret_cast<Real *>(o0.global_state) + rec * (N * 4));
+            float4 *os = reinterpret_cast<float4 *>(reinterpret_cast<Real *>(o0.obs_self) + rec * (N * 4));
+            float4 *oo = reinterpret_cast<float4 *>(reinterpret_cast<Real *>(o0.obs_others) + rec * (N * LO));
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float4 row = make_float4((float)vx[i], (float)vy[i], (float)px[i], (float)py[i]);
+                __stcs(gs + i, row);
+                __stcs(os + i, row);
+                const int j = (N == 1) ? 0 : 1 - i;   // the one other agent (N = 1: the agent itself, :148-153)
+                __stcs(oo + i, make_float4((float)Op::sub(vx[j], vx[i]), (float)Op::sub(vy[j], vy[i]),
+                                           (float)Op::sub(px[j], px[i]), (float)Op::sub(py[j], py[i])));
+            }
+            if (acts.on) act_word = acts.hand_over(t, act_loaded, lane);
+            return;
+        }
         // this step's staging set; with two sets only the stores of step t - 2 must have left it
         unsigned char *stage_row = stage_base + (Gm::kStages == 2 ? (t & 1) * Gm::kSetBytes : 0);
         unsigned char *stage_oo = stage_row + Gm::kOthOff;
         if (pending) {
-            if (lane == 0) {
+            if (leader) {
                 if (Gm::kStages == 2) bulk_wait_read_but_one(); else bulk_wait_read();
             }
         }
@@ -400,7 +438,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
         pending = false;
         if (tma) {
             // whole tiles only (B % 32 == 0): one tensor-map store per field, un-swizzling on the way out
-            if (lane == 0) {
+            if (leader) {
                 const int tile = tile_idx + t * tiles_per_slot;
 #ifndef CM3_NO_L2_HINT_TMA  // write-once stream: evict-first (see common.cuh, L2 cache policies)
                 const uint64_t pol = l2_policy_evict_first();
@@ -429,7 +467,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
             for (int d = 0; d < nd; ++d) {
                 Real *g = reinterpret_cast<Real *>(p.out[d].*field) + row0 * (size_t)per_env;
                 if (nenv == kWarp && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
-                    if (lane == 0) bulk_store(g, stage, bytes);
+                    if (leader) bulk_store(g, stage, bytes);
                     pending = true;
                 } else {
                     for (int idx = lane; idx < nenv * per_env; idx += kWarp) g[idx] = stage[idx];
@@ -439,7 +477,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
         put(&PtOut::obs_others, stage_oo, N * LO);
         put(&PtOut::global_state, stage_row, N * 4);
         put(&PtOut::obs_self, stage_row, N * 4);
-        if (lane == 0) bulk_commit();
+        if (leader) bulk_commit();
         if (acts.on) act_word = acts.hand_over(t, act_loaded, lane);
     };
 
@@ -634,7 +672,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
     }
     ticket.publish(lane);  // this tile's next launch may go ahead
     // shared memory must outlive the async reads; the global writes themselves complete with the grid
-    if (pending && lane == 0) bulk_wait_read();
+    if (pending && leader) bulk_wait_read();
 }
 
 // ------------------------------------------------------------------------ host side

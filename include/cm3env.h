@@ -46,7 +46,8 @@ typedef enum {
     CM3_ERR_BAD_SHAPE = -2,   /* geometry the reference itself rejects (checkers.py:16-17) */
     CM3_ERR_CUDA = -3,        /* a CUDA runtime call failed; message has the CUDA error */
     CM3_ERR_UNSUPPORTED = -4, /* geometry / agent count outside what the kernels address */
-    CM3_ERR_NO_DEVICE = -5    /* no CUDA device: there is no CPU fallback */
+    CM3_ERR_NO_DEVICE = -5,   /* no CUDA device: there is no CPU fallback */
+    CM3_ERR_NCCL = -6         /* cm3_comm_*: NCCL missing or an NCCL call failed */
 } cm3_status;
 
 typedef enum { CM3_REAL_F32 = 0, CM3_REAL_F64 = 1 } cm3_real;
@@ -267,9 +268,10 @@ typedef struct {
      * softplus penetration for every pair at every distance (core.py:143-155); its tail decays as
      * contact_force * contact_margin * exp(-(dist - dist_min) / contact_margin), i.e. below 1e-9
      * beyond dist_min + 18.4 contact_margin - four orders of magnitude under float32 resolution of
-     * the quantities it is added to.  Default 1e-9 (cm3_particle_default_config); 0 = skip a pair
-     * only where its force is exactly zero in float arithmetic (round 1's criterion).  The double
-     * kernels always use the exact-zero criterion. */
+     * the quantities it is added to.  Default 0 (cm3_particle_default_config) = skip a pair only where
+     * its force is exactly zero in float arithmetic, which keeps the float kernel identical to its own
+     * literal evaluation; 1e-9 measured within noise of that on every workload (warps, not lanes,
+     * skip the evaluation: profiles/r02c_ab.txt).  The double kernels always use the exact criterion. */
     double contact_cutoff;
 } cm3_particle_config;
 
@@ -366,6 +368,23 @@ int cm3_particle_rollout_host(cm3_particle_t h, const cm3_particle_state *st, co
                               int8_t *actions_dev, int32_t T, uint64_t seed, int64_t t0, int32_t auto_reset,
                               const cm3_particle_outputs *outs_dev, const void *const *dev_blocks,
                               void *host_blocks, size_t block_bytes, size_t host_stride, void *stream);
+
+/* ------------------------------------------------------------------ rollout exchange without torch */
+
+/* The all-gather of rollout buffers (BASELINE configs[3]) for bindings that have no
+ * torch.distributed: one process per GPU, NCCL underneath (resolved with dlopen at first use, so the
+ * library has no link-time NCCL dependency).  Rank 0 calls cm3_comm_unique_id and hands the 128 bytes
+ * to every other rank by its own means; all ranks then call cm3_comm_init with the same id.
+ * cm3_comm_allgather: every rank contributes `bytes_per_rank` bytes from `send`; `recv` receives
+ * world * bytes_per_rank bytes, rank r's contribution at offset r * bytes_per_rank (ncclAllGather on
+ * `stream`, asynchronous).  The reference has no counterpart (alg/train_multiprocess.py:31-43 runs
+ * independent seeds).  The fused alternative - the step kernel storing straight into the peers'
+ * buffers - is cm3_*_rollout_gather. */
+typedef struct cm3_comm_s *cm3_comm_t;
+int cm3_comm_unique_id(uint8_t *id /* [128] */);
+int cm3_comm_init(const uint8_t *id /* [128] */, int32_t rank, int32_t world, int32_t device, cm3_comm_t *out);
+int cm3_comm_allgather(cm3_comm_t c, const void *send, void *recv, size_t bytes_per_rank, void *stream);
+int cm3_comm_destroy(cm3_comm_t c);
 
 #ifdef __cplusplus
 }
