@@ -45,6 +45,7 @@ SEED = 12341        # alg/config.json:6
 MAX_STEPS = 33      # alg/config.json:61
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 NVLINK_PEER_GBS = 770.0    # B200_PROFILING.md: measured peer copy, per direction per GPU (900 nominal)
+FUSED_T = int(os.environ.get("CM3_BENCH_FUSED_T", "0"))  # experiment: steps per fused launch in measure_workload (0 = one episode)
 SPIN_CYCLES = 4_000_000    # ~2 ms of device spin queued ahead of a timed region (see timed_steps)
 
 
@@ -396,7 +397,7 @@ def measure_workload(spec, wl, B, K, W, rank, world, device, local_rank, peak, m
     action stream from HBM, then one chained launch per step from a CUDA graph.  Returns a dict of
     whole-job numbers (max over ranks)."""
     import torch
-    T = MAX_STEPS
+    T = FUSED_T or MAX_STEPS
     env = make_env(spec, B, device, env_id_offset=rank * B)
     bpe = bytes_per_env_step(env)
     res = {"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"], "n_gpus": world,

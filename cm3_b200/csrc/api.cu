@@ -84,6 +84,19 @@ int chain_parts(int ntiles) {
     return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
 }
 
+// Off by default: measured slower than one thread per env on the fused rollout (profiles/r02h_ab.txt)
+bool pair_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_PT_PAIR");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+
+// two-agent envs run one lane per agent (16 envs per warp); the sync words are sized for that tiling
+// whichever kernel ends up stepping them
+int particle_tile_envs(int N) { return N == 2 ? kWarp / 2 : kWarp; }
+
 bool dyn_geometry_forced() {
     static const bool on = [] {
         const char *v = getenv("CM3_CK_DYNAMIC");
@@ -667,7 +680,8 @@ int cm3_particle_destroy(cm3_particle_t h) {
 
 int cm3_particle_tiles(cm3_particle_t h, int32_t *tiles) {
     if (!h || !tiles) { set_error("handle/tiles is NULL"); return CM3_ERR_BAD_ARG; }
-    *tiles = (h->cfg.num_envs + kWarp - 1) / kWarp;
+    const int ew = particle_tile_envs(h->cfg.n_agents);
+    *tiles = (h->cfg.num_envs + ew - 1) / ew;
     return CM3_OK;
 }
 

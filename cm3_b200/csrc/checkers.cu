@@ -167,9 +167,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     const uint64_t kFull = (R * C >= 64) ? ~0ull : ((1ull << (R * C)) - 1ull);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // the one thread that issues, commits and waits for this warp's bulk stores (elect.sync: ptxas then
-    // knows a single thread is active and needs no operand loop around the TMA instructions)
-    const bool leader = elect_one();
+    const bool leader = elect_one();  // issues, commits and waits for this warp's bulk stores (common.cuh)
     const int tile = p.tile0 + blockIdx.x * kCkWarpsPerBlock + warp;
     // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
     TileTicket ticket;

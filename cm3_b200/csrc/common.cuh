@@ -103,9 +103,21 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return pol;
 }
 
-// one thread of the (fully active) warp, in a form ptxas understands as "exactly one thread": the
-// uniform-register operands of a TMA instruction issued under this predicate need no waterfall loop
+// The thread of a warp that issues, commits and waits for its TMA stores.  Default: lane 0.
+// Measured and dropped (round 2, profiles/r02g_ab.txt): electing it with elect.sync, which lets ptxas
+// see that a single thread is active - under `if (lane == 0)` it wraps every TMA instruction in a
+// loop that moves the uniform-register operands over one distinct value at a time, ~15 instructions
+// per store.  The elected variant executes ~45 fewer instructions per particle step and is SLOWER on
+// the same box, every time: PA4 0.869 vs 0.905 of the roofline, PA3 0.824 vs 0.856, CK1 0.904 vs
+// 0.913 (CK2, PM2 within noise).  The back-to-back store issue apparently costs more than the
+// operand loops did.  CM3_ELECT=1 rebuilds it.
+#ifndef CM3_ELECT
+#define CM3_ELECT 0
+#endif
 __device__ __forceinline__ bool elect_one() {
+#if !CM3_ELECT
+    return (threadIdx.x & 31) == 0;
+#endif
     uint32_t pred;
     asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
     return pred != 0;

@@ -102,6 +102,9 @@ int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaSt
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);
+int particle_pair_launch(int real, const PtParams &p, cudaStream_t stream);  // particle_pair.cu: N = 2, one lane per agent
+bool pair_enabled();            // CM3_PT_PAIR=1 sends two-agent envs through the one-lane-per-agent kernel (experiment, off)
+int particle_tile_envs(int N);  // envs per warp tile (the granularity of cm3_particle_state.sync)
 bool full_enabled();  // particle kernel: the specialised all-outputs / whole-tiles instantiation (CM3_PT_FULL=0 disables)
 bool tma_enabled();  // swizzled tiles + tensor-map stores in the particle kernel (CM3_TMA=0 disables)
 bool pdl_enabled();  // programmatic dependent launch between consecutive step launches (CM3_PDL=0 disables)

@@ -196,3 +196,43 @@ def test_evaluate_episodes_matches_the_reference_evaluation_loop():
     np.testing.assert_allclose(rl.cpu().numpy(), loc.mean(axis=0), rtol=1e-7)
     np.testing.assert_allclose(float(rg), glob.mean(), rtol=1e-7)
     assert length.min() < 50 < length.max() + 1  # early all-reached endings and max_steps endings
+
+
+def test_collected_particle_episodes_are_filed_good_or_bad_like_the_trainer_files_them():
+    """train_onpolicy.py:329-356 on the device: the collector's transitions go through the episode
+    router into the dual buffer; every transition must end up in memory_1 exactly when the episode it
+    belongs to ended with scenario.collisions != 0 (the per-step `collisions` output, latched before
+    the in-kernel reset).  Checked per env against a scan of done / collisions on the host."""
+    from cm3_b200.replay import DeviceDualReplayBuffer, EpisodeRouter
+    B, T, blocks = 256, 40, 3
+    env = VecParticle(B, 2, presets.PARTICLE["merge"], max_steps=presets.MAX_STEPS)
+    col = TransitionCollector(env, seed=5)
+    col.reset()
+    router, buf = EpisodeRouter(), DeviceDualReplayBuffer(size=10 ** 6)
+    dones, colls, uids = [], [], []
+    for k in range(blocks):
+        tr = col.collect(T)
+        uid = (torch.arange(T, device=env.device).unsqueeze(1) + k * T) * B + torch.arange(B, device=env.device)
+        fields = {f: tr[f] for f in ("global_state", "obs_others", "obs_self", "actions", "reward", "reward_n",
+                                     "global_state_next", "obs_others_next", "obs_self_next", "done", "goals")}
+        fields["uid"] = uid
+        ready, bad = router.push(fields, tr["done"], tr["collisions"])
+        if ready:
+            buf.add(ready, bad)
+        dones.append(tr["done"].cpu().numpy()); colls.append(tr["collisions"].cpu().numpy()); uids.append(uid.cpu().numpy())
+    done, coll, uid = np.concatenate(dones), np.concatenate(colls), np.concatenate(uids)
+    want_bad, want_good = set(), set()
+    for b in range(B):
+        ep = []
+        for t in range(T * blocks):
+            ep.append(int(uid[t, b]))
+            if done[t, b]:
+                (want_bad if coll[t, b] != 0 else want_good).update(ep)
+                ep = []
+    got_bad = set(buf.memory_1.take()["uid"].tolist()) if len(buf.memory_1) else set()
+    got_good = set(buf.memory_2.take()["uid"].tolist()) if len(buf.memory_2) else set()
+    assert got_bad == want_bad and got_good == want_good
+    assert want_bad and want_good                      # merge with random actions produces both kinds
+    batch = buf.sample_batch(64)                       # half from each memory, memory_1 part first
+    assert batch["uid"].shape[0] == 64 and set(batch["uid"][:32].tolist()) <= want_bad and set(batch["uid"][32:].tolist()) <= want_good
+    assert batch["obs_others"].shape == (64, 2, 4)
