@@ -84,6 +84,15 @@ int chain_parts(int ntiles) {
     return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
 }
 
+// Off by default: measured slower than one env per thread (profiles/r02k_ab.txt, r02l_ab.txt)
+bool duo_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("CM3_PT_DUO");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+
 // Off by default: measured slower than one thread per env on the fused rollout (profiles/r02h_ab.txt)
 bool pair_enabled() {
     static const bool on = [] {

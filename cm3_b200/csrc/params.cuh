@@ -103,6 +103,9 @@ int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStrea
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);
 int particle_pair_launch(int real, const PtParams &p, cudaStream_t stream);  // particle_pair.cu: N = 2, one lane per agent
+constexpr int kDuoNotMine = 1;  // particle_duo_launch: "not my case", as opposed to a cm3_status
+int particle_duo_launch(int N, int real, const PtParams &p, cudaStream_t stream);  // particle_duo.cu: N <= 2, two envs per thread
+bool duo_enabled();             // CM3_PT_DUO=1 sends the common launch of one- and two-agent envs through the two-envs-per-thread kernel (experiment, off)
 bool pair_enabled();            // CM3_PT_PAIR=1 sends two-agent envs through the one-lane-per-agent kernel (experiment, off)
 int particle_tile_envs(int N);  // envs per warp tile (the granularity of cm3_particle_state.sync)
 bool full_enabled();  // particle kernel: the specialised all-outputs / whole-tiles instantiation (CM3_PT_FULL=0 disables)

@@ -42,45 +42,6 @@
 
 namespace cm3 {
 
-// 16-byte chunks per env record S = odd * 2^k: lanes one record apart collide on the 8 bank groups
-// unless the 16-byte chunk index is XOR-ed with higher address bits; k = 0 needs no swizzle,
-// k = 1 / 2 / >= 3 the TMA 32- / 64- / 128-byte swizzle (conflict-free for every S, checked
-// exhaustively in tests/test_particle_layout.py).
-__host__ __device__ constexpr int sw_bits_for(int chunks) {
-    // (128-byte rows everywhere - fewer, wider TMA rows at the price of 2- to 3-way conflicts for
-    // S = 6, 12 - measured within +-1.5 % of this choice: profiles/r01l_ab.txt, r01w)
-    return (chunks % 2) ? 0 : (chunks % 4) ? 1 : (chunks % 8) ? 2 : 3;
-}
-__host__ __device__ constexpr int sw_row_bytes(int bits) { return bits ? (16 << bits) : 128; }
-
-template <int N, typename Real>
-struct PtGeom {
-    static constexpr int NO = (N > 1) ? N - 1 : 1;  // "other" agents per agent
-    static constexpr int LO = 4 * NO;
-    static constexpr int kRowBytes = kWarp * N * 4 * (int)sizeof(Real);   // global_state / obs_self tile
-    static constexpr int kOthBytes = kWarp * N * LO * (int)sizeof(Real);  // obs_others tile
-    static constexpr int kRowSw = sw_bits_for(N * 4 * (int)sizeof(Real) / 16);
-    static constexpr int kOthSw = sw_bits_for(N * LO * (int)sizeof(Real) / 16);
-    static constexpr uint32_t kRowMask = ((1u << kRowSw) - 1u) << 4;  // bits [4, 4+sw) ^= bits [7, 7+sw)
-    static constexpr uint32_t kOthMask = ((1u << kOthSw) - 1u) << 4;
-    static constexpr int kRowW = sw_row_bytes(kRowSw), kOthW = sw_row_bytes(kOthSw);  // tensor-map row widths
-    static constexpr int kRowRows = kRowBytes / kRowW, kOthRows = kOthBytes / kOthW;  // box rows per tile
-    static constexpr int kOthOff = round_up(kRowBytes, 1024);  // swizzle patterns repeat every 1024 bytes
-    // One staging set = row tile + others tile.  Two sets (double-buffered staging: the stores of
-    // step t drain while step t + 1 is staged into the other set) for N <= 2, where a step is short
-    // compared with the time a store takes to drain: measured +12 % for PM2, -3 % for PA3
-    // (profiles/r01r_ab.txt); PA4's 8 KB sets would not fit twice in the 14 blocks per SM of the
-    // one-wave 65 536-env batch anyway.
-    static constexpr int kSetBytes = round_up(kOthOff + kOthBytes, 1024);
-    static constexpr int kOverhead = ActionStream<N>::kSmemBytes + 1024 /* alignment slack */;
-    static constexpr int kStages = (N <= 2 && 14 * (2 * kSetBytes + kOverhead + 1024 /* driver-reserved */) <= 227 * 1024) ? 2 : 1;
-    static constexpr int kActOff = kStages * kSetBytes;             // ActionStream slots
-    static constexpr int kSmemBytes = kActOff + kOverhead;
-    // a TMA box has at most 256 rows: the wide records of N >= 6 (and N = 5..8 in double) do not fit
-    // one box per tile and take the linear tile + plain bulk stores instead
-    static constexpr bool kTmaOk = kRowRows <= 256 && kOthRows <= 256;
-};
-
 // Measured and dropped (round 2, profiles/r02d_ab.txt): float kernels with at most two agents storing
 // their observation records straight from registers (16-byte streaming stores, no staging, no TMA, no
 // drain wait - see emit).  The records of a warp are contiguous, but every store instruction fills
@@ -522,7 +483,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
 
 // A [T][out_B] output field seen as a 2-D byte tensor of `width`-byte rows; one box = the tile of
 // 32 consecutive envs.  The swizzle mode is the one the kernel staged the tile in.
-static bool encode_tile_map(CUtensorMap *tm, void *base, size_t total_bytes, int sw_bits, int width, int box_rows) {
+bool encode_tile_map(CUtensorMap *tm, void *base, size_t total_bytes, int sw_bits, int width, int box_rows) {
     static const PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -600,6 +561,10 @@ static int dispatch_pt(const PtParams &p0, cudaStream_t stream) {
 
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream) {
     if (N == 2 && pair_enabled()) return particle_pair_launch(real, p, stream);
+    if (N <= 2 && duo_enabled()) {  // the common launch of small envs: two envs per thread (particle_duo.cu)
+        const int rc = particle_duo_launch(N, real, p, stream);
+        if (rc != kDuoNotMine) return rc;
+    }
 #define CASE(n) \
     case n: return real == CM3_REAL_F64 ? dispatch_pt<n, double>(p, stream) : dispatch_pt<n, float>(p, stream);
     switch (N) {

@@ -431,29 +431,25 @@ def test_planned_rollout_equals_rollout(game):
         a.plan_rollout(T, actions=acts.to(torch.int32))
 
 
-# ---------------------------------------------------------------------------------- N = 2: one lane per agent
-@pytest.mark.parametrize("dtype", ["float32", "float64"])
-def test_pair_kernel_is_bit_identical_to_the_thread_per_env_kernel(dtype, tmp_path):
-    """The one-lane-per-agent variant for two-agent envs (particle_pair.cu, CM3_PT_PAIR=1) performs the
-    same operations in the same order as the default one-thread-per-env kernel: every output of
-    a reset, single steps (ragged batch), a fused rollout with in-kernel resets and Philox actions,
-    and the final state must be IDENTICAL bit for bit."""
-    code = r"""
+# ---------------------------------------------------------------------------------- N <= 2: kernel variants
+_DUMP_CODE = r"""
 import sys
 sys.path[:0] = [%r]
 import numpy as np, torch
 from cm3_b200 import VecParticle, presets
 dt = getattr(torch, %r)
+N = %d
+cfg = presets.PARTICLE["merge"] if N == 2 else presets.PARTICLE["stage1"]
 out = {}
-for B in (1000, 4096):
-    env = VecParticle(B, 2, presets.PARTICLE["merge"], prob_random=0.3, max_steps=9, dtype=dt, env_id_offset=77)
+for B in %r:
+    env = VecParticle(B, N, cfg, prob_random=0.3, max_steps=9, dtype=dt, env_id_offset=77)
     o = env.reset(seed=5)
     for k, v in o.items():
         if k not in ("reward", "reward_n", "collisions", "reached"):
             out["reset_%%d_%%s" %% (B, k)] = v.cpu().numpy().copy()
     rng = np.random.default_rng(B)
     for t in range(12):
-        a = rng.integers(0, 5, size=(B, 2)).astype(np.int8)
+        a = rng.integers(0, 5, size=(B, N)).astype(np.int8)
         if t %% 3 == 0:
             a[::7] = 9
         o = env.step(a)
@@ -462,23 +458,52 @@ for B in (1000, 4096):
     ro = env.rollout(40, seed=3, t0=100, auto_reset=True, record_actions=True)
     for k, v in ro.items():
         out["roll_%%d_%%s" %% (B, k)] = v.cpu().numpy().copy()
-    acts = rng.integers(0, 5, size=(20, B, 2)).astype(np.int8)
+    acts = rng.integers(0, 5, size=(20, B, N)).astype(np.int8)
     ro = env.rollout(20, actions=acts, seed=3, t0=140, auto_reset=True)
     for k, v in ro.items():
         out["roll2_%%d_%%s" %% (B, k)] = v.cpu().numpy().copy()
+    # chained single-step launches into a ring, after plain launches on the same state
+    ring = env.alloc_outputs(6)
+    dacts = torch.from_numpy(acts[:6]).to(env.device)
+    for t in range(6):
+        env.step_chained(dacts[t], {k: v[t] for k, v in ring.items()}, seed=3, t0=200 + t, auto_reset=True)
+    for k, v in ring.items():
+        out["chain_%%d_%%s" %% (B, k)] = v.cpu().numpy().copy()
     for k, v in env.state.items():
         out["state_%%d_%%s" %% (B, k)] = v.cpu().numpy().copy()
 np.savez(sys.argv[1], **out)
 print("dumped", len(out))
-""" % (ROOT, dtype)
+"""
+
+
+def _variants_agree(tmp_path, dtype, N, batches, env_a, env_b):
     res = {}
-    for tag, val in (("pair", "1"), ("thread", "0")):
+    for tag, env in (("a", env_a), ("b", env_b)):
         path = str(tmp_path / (tag + ".npz"))
-        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, CM3_PT_PAIR=val), capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, "-c", _DUMP_CODE % (ROOT, dtype, N, batches), path], env=dict(os.environ, **env),
+                           capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "dumped" in r.stdout, r.stdout + r.stderr
         res[tag] = np.load(path)
-    assert set(res["pair"].files) == set(res["thread"].files) and len(res["pair"].files) > 50
-    for k in res["pair"].files:
-        a, b = res["pair"][k], res["thread"][k]
+    assert set(res["a"].files) == set(res["b"].files) and len(res["a"].files) > 50
+    for k in res["a"].files:
+        a, b = res["a"][k], res["b"][k]
         assert a.dtype == b.dtype and a.shape == b.shape, k
         assert np.array_equal(a, b, equal_nan=True), (k, int((a != b).sum()))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_pair_kernel_is_bit_identical_to_the_thread_per_env_kernel(dtype, tmp_path):
+    """The one-lane-per-agent variant for two-agent envs (particle_pair.cu, CM3_PT_PAIR=1) performs the
+    same operations in the same order as the one-thread-per-env kernel: every output of a reset,
+    single steps (ragged batch), fused rollouts with in-kernel resets (Philox and given actions),
+    chained steps and the final state must be IDENTICAL bit for bit."""
+    _variants_agree(tmp_path, dtype, 2, (1000, 4096), dict(CM3_PT_PAIR="1", CM3_PT_DUO="0"), dict(CM3_PT_PAIR="0", CM3_PT_DUO="0"))
+
+
+@pytest.mark.parametrize("N", [1, 2])
+def test_duo_kernel_is_bit_identical_to_the_thread_per_env_kernel(N, tmp_path):
+    """The two-envs-per-thread variant for the common launch of one- and two-agent envs
+    (particle_duo.cu, CM3_PT_DUO=1; whole 64-env tiles, float, all outputs) against the default
+    one-env-per-thread kernel: identical bits, including launches that alternate between the two kernels on one
+    state (resets and the ragged batch always take particle.cu) and chained steps."""
+    _variants_agree(tmp_path, "float32", N, (4096, 1000, 64), dict(CM3_PT_DUO="1"), dict(CM3_PT_DUO="0"))
