@@ -67,6 +67,14 @@ def workload_spec(name):
     raise SystemExit("unknown workload %r" % name)
 
 
+def workload_config(spec, B, l2="n/a (host memory)"):
+    """The `config` of the JSON line: the workload, under the same keys for the GPU arm and the reference arm."""
+    return {"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"],
+            "actions": "uniform integers in 0..4, a [33][B][N] stream generated before the timed region and read by every step",
+            "episodes": "max_steps 33; an env whose step returns done starts a fresh episode",
+            "l2": l2}
+
+
 def make_env(spec, B, device, env_id_offset=0):
     from cm3_b200 import VecCheckers, VecParticle
     if spec["kind"] == "checkers":
@@ -207,9 +215,6 @@ class StepRunner(object):
         g = torch.Generator(device="cpu").manual_seed(seed)
         acts = torch.randint(0, 5, (ring, env.B, env.N), generator=g, dtype=torch.int8)
         self.actions = acts.to(env.device)
-        # everything a launch needs is built here, once: per-slot output structs and action slices
-        self.slots = [env._outputs_struct({k: v[t] for k, v in self.ring_out.items()}) for t in range(ring)]
-        self.acts = [self.actions[t] for t in range(ring)]
         self.graph = None
         self.launches = 0
 
@@ -217,13 +222,17 @@ class StepRunner(object):
         # one kernel launch: one step with in-kernel episode reset, outputs -> ring slot
         i = t % self.ring
         if self.chained:
-            self.env.step_chained(self.acts[i], self.slots[i], seed=SEED, t0=t, auto_reset=True)
+            self.env.step_chained(self.actions[i], {k: v[i] for k, v in self.ring_out.items()}, seed=SEED, t0=t, auto_reset=True)
         else:
             self.env.rollout(1, actions=self.actions[i:i + 1], auto_reset=True, t0=t,
                              out={k: v[i:i + 1] for k, v in self.ring_out.items()})
 
     def capture(self):
         torch = self.torch
+        if self.chained:  # the facade's own captured form (cm3_b200/graph.py)
+            from cm3_b200.graph import ChainedStepGraph
+            self.graph = ChainedStepGraph(self.env, self.actions, self.ring_out, seed=SEED, auto_reset=True).graph
+            return
         self.graph = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(device=self.env.device)
         s.wait_stream(torch.cuda.current_stream(self.env.device))
@@ -488,18 +497,18 @@ def run_gpu(args):
     kernel_key = "%s_%s" % (args.workload, "step" if mode.startswith("step") else "rollout")
     kname = KERNEL_NAMES[args.workload]
 
-    config = dict({"workload": spec["label"] % B, "envs_per_gpu": B, "n_agents": spec["n"], "mode": mode,
-                   "actions": "uniform int8 in 0..4, a [33][B][N] stream pre-generated in HBM and read by every step",
-                   "auto_reset": True,
-                   "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world,
-                   "timing": "CUDA events on the launching stream behind a %d-cycle device spin (all launches enqueued before the first event fires); barrier + synchronize both sides; max over ranks" % SPIN_CYCLES},
-                  **launch_cfg)
+    config = workload_config(spec, B, launch_cfg.pop("l2"))
+    launch_config = dict({"mode": mode, "actions": "int8 in HBM", "auto_reset": "in-kernel",
+                          "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world,
+                          "timing": "CUDA events on the launching stream behind a %d-cycle device spin (all launches enqueued before the first event fires); barrier + synchronize both sides; max over ranks" % SPIN_CYCLES},
+                         **launch_cfg)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 bitboard state, f32 outputs" if spec["kind"] == "checkers" else "f32",
         "data": "synthetic",
         "config": config,
+        "launch_config": launch_config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(kernel_key),
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": eff_bpe,
@@ -511,10 +520,12 @@ def run_gpu(args):
     if gather_mode is not None:
         sent = out_b * B * (world - 1)  # bytes this GPU delivers to its peers per env step
         out["gpu_launches"] = K // T
-        out["config"].update({"launch": "1 launch per %d fused env steps, device Philox actions" % T,
+        out["config"]["actions"] = "Philox4x32-10 on the device, keyed by (seed, global env id, step)"
+        out["launch_config"].update({"launch": "1 launch per %d fused env steps, device Philox actions" % T,
                               "actions": "Philox4x32-10 on the device, keyed by (seed, global env id, step)",
                               "rollout_all_gather": gather_mode, "overlap": "two symmetric buffers: rollout k+1 runs while the stores of rollout k drain" if not args.no_overlap else "none",
-                              "l2": "gathered rollout buffer [%d][%d envs] = %.0f MB per GPU (> 126 MB L2 when >= 2 GPUs at the default size)" % (T, world * B, out_b * world * B * T / 1e6)})
+                              })
+        out["config"]["l2"] = "gathered rollout buffer [%d][%d envs] = %.0f MB per GPU (> 126 MB L2 when >= 2 GPUs at the default size)" % (T, world * B, out_b * world * B * T / 1e6)
         out["roofline"] = gather_roofline(out_b, state_b, T, B, world, step_us, peak, peak_src, kname, gather_mode)
     else:
         out["e2e"] = measure_e2e(spec, args, world, rank, device)   # all ranks take part
@@ -824,12 +835,11 @@ def run_reference(args):
         "n_gpus": world, "steps": done_steps, "warmup": W,
         "ms_per_step": el * 1e3 / done_steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        # same keys as the GPU arm's config (the driver compares them)
-        "config": {"workload": spec["label"] % args.envs, "envs_per_gpu": args.envs, "n_agents": spec["n"], "mode": "cpu",
-                   "actions": "uniform int in 0..4, a [33][B][N] stream pre-generated in host memory and read by every step",
-                   "auto_reset": True, "parallelism": "OpenMP over envs, %d host threads, one process" % nthreads,
-                   "timing": "time.perf_counter around the timed steps", "launch": "one C call per step",
-                   "l2": "n/a", "sample": sample},
+        # the same workload description as the GPU arm prints (the driver compares the two)
+        "config": workload_config(spec, args.envs),
+        "launch_config": {"mode": "cpu", "parallelism": "OpenMP over envs, %d host threads, one process" % nthreads,
+                          "timing": "time.perf_counter around the timed steps", "launch": "one C call per step; caller-side reset every 33 steps",
+                          "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -19,7 +19,8 @@ NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPI
 
 
 def library_path():
-    """The in-tree library; CM3ENV_LIBRARY selects an experimental build (tools/build_variants.py)."""
+    """The in-tree library; CM3ENV_LIBRARY selects an experimental build (build_library(defines=..., output=...),
+    compared with tools/ab_r02.py)."""
     return os.environ.get("CM3ENV_LIBRARY") or os.path.join(CSRC, "libcm3env.so")
 
 

@@ -507,3 +507,33 @@ def test_duo_kernel_is_bit_identical_to_the_thread_per_env_kernel(N, tmp_path):
     one-env-per-thread kernel: identical bits, including launches that alternate between the two kernels on one
     state (resets and the ragged batch always take particle.cu) and chained steps."""
     _variants_agree(tmp_path, "float32", N, (4096, 1000, 64), dict(CM3_PT_DUO="1"), dict(CM3_PT_DUO="0"))
+
+
+@pytest.mark.parametrize("game", ["ck2", "pa4"])
+def test_chained_step_graph_replays_continue_the_trajectory(game):
+    """cm3_b200.graph.ChainedStepGraph: `ring` chained steps captured once; every replay continues the
+    episodes exactly like the fused rollout over the same actions does (constructing the graph leaves
+    no trace in the env state)."""
+    from cm3_b200.graph import ChainedStepGraph
+    B, ring = 2048, 16
+    rng = np.random.default_rng(4)
+    if game == "ck2":
+        a, b = VecCheckers(B, **CK2), VecCheckers(B, **CK2)
+        a.reset(goals=np.eye(2)); b.reset(goals=np.eye(2))
+        fields = CK_REF
+    else:
+        a, b = VecParticle(B, 4, ANTI, max_steps=7), VecParticle(B, 4, ANTI, max_steps=7)
+        a.reset(seed=2); b.reset(seed=2)
+        fields = PT_REF
+    acts = torch.from_numpy(rng.integers(0, 5, size=(ring, B, a.N)).astype(np.int8)).to(a.device)
+    g = ChainedStepGraph(a, acts, a.alloc_outputs(ring, fields=fields), seed=9, t0=0, auto_reset=True)
+    for k in a.state:
+        assert torch.equal(a.state[k], b.state[k]), k
+    for rep in range(3):
+        got = g.replay()
+        want = b.rollout(ring, actions=acts, seed=9, t0=0, auto_reset=True)
+        torch.cuda.synchronize()
+        for f in fields:
+            assert torch.equal(got[f], want[f]), (game, rep, f)
+    with pytest.raises(ValueError):
+        ChainedStepGraph(a, acts[:1].contiguous(), a.alloc_outputs(1, fields=fields))

@@ -13,7 +13,7 @@ def main():
             continue
         r = d.get("roofline", {})
         print("%s: n=%s mode=%s K=%s value=%.4g us/step=%.3f frac=%.3f launches=%s per_rank_ms=%s" % (
-            f.split("/")[-1], d.get("n_gpus"), d.get("config", {}).get("mode"), d.get("steps"), d["value"],
+            f.split("/")[-1], d.get("n_gpus"), d.get("launch_config", d.get("config", {})).get("mode"), d.get("steps"), d["value"],
             d["ms_per_step"] * 1e3, r.get("frac", float("nan")), d.get("gpu_launches"),
             ["%.3f" % x for x in d.get("per_rank_ms", [])]))
         c = d.get("clocks") or {}
