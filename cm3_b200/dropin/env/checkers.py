@@ -27,6 +27,10 @@ class Checkers(object):
         self._vec = VecCheckers(1, n_rows, n_columns, n_obs, list(agents_r)[:n_agents],
                                 list(agents_c)[:n_agents], n_agents, max_steps, device=device,
                                 dtype=torch.float64)
+        import ctypes
+        # the reference's trainers never switch CUDA streams: the handle of the stream current at
+        # construction is cached, one attribute look-up less on the per-step path
+        self._stream = ctypes.c_void_p(torch.cuda.current_stream(self._vec.device).cuda_stream)
 
     # ------------------------------------------------------------------ tuple assembly
     _OBS = ("grid", "vec", "obs_others", "obs_self_t", "obs_self_v")
@@ -61,9 +65,10 @@ class Checkers(object):
         a = np.asarray(actions).reshape(1, self.n_agents)
         # one launch + one stream wait: the kernel reads the actions from and writes every field to
         # pinned host memory directly (VecCheckers.step_mapped)
-        o = self._host(self._vec.step_mapped(a), self._OBS + ("reward", "local_rewards", "done"))
-        local_rewards = [float(x) for x in o["local_rewards"]]
-        return self._obs_tuple(o) + (np.float64(o["reward"]), local_rewards, bool(o["done"]))
+        v = self._vec.step_mapped(a, stream=self._stream, copy=True)   # views of one fresh host copy
+        o = {f: v[f][0] for f in self._OBS}
+        local_rewards = [float(x) for x in v["local_rewards"][0]]
+        return self._obs_tuple(o) + (np.float64(v["reward"][0]), local_rewards, bool(v["done"][0]))
 
     # ------------------------------------------------------------------ read-only views of state
     def _observe(self):

@@ -70,6 +70,12 @@ class MultiAgentEnv(object):
         self._results = None
         self._handed_out = None
         self._fresh = False
+        # stock callbacks: the bound methods of the scenario itself, not overridden on the instance
+        self._stock_callbacks = all(getattr(cb, "__func__", None) is getattr(type(scenario), name, None)
+                                    for cb, name in ((reward_callback, "reward"), (observation_callback, "observation"),
+                                                     (done_callback, "done")))
+        import ctypes
+        self._stream = ctypes.c_void_p(torch.cuda.current_stream(self._vec.device).cuda_stream)
         scenario._env = self
         self._upload_world()   # make_world() already drew an initial state (multi-goal_spread.py:62)
 
@@ -125,18 +131,20 @@ class MultiAgentEnv(object):
         if self._stale():
             self._upload_world()
 
-    def _adopt(self, views, with_reward):
-        """Takes the results of the last launch (windows of the pinned host mirror, one device-to-host
-        copy) into the entity objects and the scenario."""
+    def _adopt(self, views, with_reward, fresh=False):
+        """Takes the results of the last launch into the entity objects and the scenario.  `views`:
+        windows of the pinned host mirror (copied out here), or with fresh=True of a host copy that is
+        already this call's own."""
         fields = ("global_state", "obs_others", "obs_self", "done") + (("reward", "reward_n", "collisions", "reached") if with_reward else ())
-        res = {f: views[f][0].copy() for f in fields}
+        res = {f: (views[f][0] if fresh else views[f][0].copy()) for f in fields}
         if not with_reward:
             res["reward"] = res["reward_n"] = None
         gs = res["global_state"]
         gs.flags.writeable = False
         for i, agent in enumerate(self.world.agents):
-            agent.state.p_vel = gs[i, 0:2]
-            agent.state.p_pos = gs[i, 2:4]
+            st = agent.state
+            st.p_vel = gs[i, 0:2]
+            st.p_pos = gs[i, 2:4]
         if with_reward:   # a reset / observe-only launch leaves reached and the counter as they are
             reached = int(res["reached"])
             for i, agent in enumerate(self.world.agents):
@@ -169,18 +177,27 @@ class MultiAgentEnv(object):
         self.steps += 1
         # one launch + one stream wait: the kernel reads the actions from and writes every field (and
         # the reached / collision flags) to pinned host memory directly (VecParticle.step_mapped)
-        res = self._adopt(self._vec.step_mapped(a), with_reward=True)
-        obs_n, obs_others_n, reward_n, done_n = [], [], [], []
-        self._fresh = True          # nothing can have touched the entities since _adopt: the
-        try:                        # callbacks below skip the staleness check
-            for agent in self.agents:   # callback order of environment.py:95-104
-                obs_self, obs_others = self._get_obs(agent)
-                obs_n.append(obs_self)
-                obs_others_n.append(obs_others)
-                reward_n.append(self._get_reward(agent))
-                done_n.append(self._get_done(agent))
-        finally:
-            self._fresh = False
+        res = self._adopt(self._vec.step_mapped(a, stream=self._stream, copy=True), with_reward=True, fresh=True)
+        if self._stock_callbacks:
+            # The callbacks are the scenario's own methods (checked in the constructor), whose results ARE
+            # the kernel's outputs: hand them out directly, in the order environment.py:95-104 calls them
+            obs_all, oth_all, rew_all = res["obs_self"], res["obs_others"], res["reward_n"]
+            obs_n = [obs_all[i].copy() for i in range(self.n)]
+            obs_others_n = [oth_all[i].copy() for i in range(self.n)]
+            reward_n = [rew_all[i] for i in range(self.n)]
+            done_n = [agent.reached for agent in self.agents]
+        else:
+            obs_n, obs_others_n, reward_n, done_n = [], [], [], []
+            self._fresh = True          # nothing can have touched the entities since _adopt: the
+            try:                        # callbacks below skip the staleness check
+                for agent in self.agents:   # callback order of environment.py:95-104
+                    obs_self, obs_others = self._get_obs(agent)
+                    obs_n.append(obs_self)
+                    obs_others_n.append(obs_others)
+                    reward_n.append(self._get_reward(agent))
+                    done_n.append(self._get_done(agent))
+            finally:
+                self._fresh = False
         reward = np.float64(res["reward"])   # np.sum(reward_n), evaluated on the device in index order
         global_state = res["global_state"].copy()
         done = bool(res["done"])

@@ -294,11 +294,13 @@ class VecCheckers(object):
                                                 C.byref(oh), self._stream()))
         return {f: self._host[f].numpy() for f in fields}
 
-    def step_mapped(self, actions):
+    def step_mapped(self, actions, stream=None, copy=False):
         """Low-latency host step for small batches (the B = 1 drop-ins): the kernel reads the
         actions from, and writes every output field to, PINNED HOST memory directly (unified
         addressing), so the host path is one launch and one stream wait - no copy calls.  Returns
-        field -> NumPy view of the pinned buffers (overwritten by the next call)."""
+        field -> NumPy view of the pinned buffers (overwritten by the next call), or with copy=True
+        views of ONE fresh host copy of the whole output block (what the B = 1 drop-ins hand out).
+        `stream`: a cached ctypes stream handle (default: torch's current stream)."""
         m = self._mapped
         if m is None:
             host = self.alloc_outputs(pinned_host=True)
@@ -307,12 +309,19 @@ class VecCheckers(object):
                                     views={f: host[f].numpy() for f in FIELDS}, step=self.lib.cm3_checkers_step,
                                     sync=self.lib.cm3_stream_synchronize, st=C.byref(self._st), a=_ptr(acts))
             m["ocr"] = C.byref(m["oc"])
+            m["block_np"] = host.block.numpy()
+            shapes = self.field_shapes()
+            m["layout"] = [(f, host.offsets[f], int(np.prod(shapes[f])) * self.field_dtype(f).itemsize,
+                            host[f].numpy().dtype, tuple(shapes[f])) for f in FIELDS]
         m["acts_np"][...] = _to_int8_host(actions, (self.B, self.N))
-        s = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        s = stream if stream is not None else C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         rc = m["step"](self._h, m["st"], m["a"], m["ocr"], s) or m["sync"](s)
         if rc != 0:
             L.check(rc)
-        return m["views"]
+        if not copy:
+            return m["views"]
+        blk = m["block_np"].copy()
+        return {f: blk[off:off + n].view(dt).reshape(shape) for f, off, n, dt, shape in m["layout"]}
 
     def download(self):
         """The packed single-step outputs (whatever the last launch wrote to self.out) in ONE
