@@ -78,7 +78,7 @@ def workload_config(spec, B, l2="n/a (host memory)"):
 def make_env(spec, B, device, env_id_offset=0):
     from cm3_b200 import VecCheckers, VecParticle
     if spec["kind"] == "checkers":
-        env = VecCheckers(B, device=device, env_id_offset=env_id_offset, **spec["ctor"])
+        env = VecCheckers(B, device=device, env_id_offset=env_id_offset, tile_dtype=spec.get("tile_dtype"), **spec["ctor"])
         env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
     else:
         env = VecParticle(B, spec["n"], spec["cfg"], prob_random=spec["prob_random"], max_steps=MAX_STEPS,
@@ -620,6 +620,22 @@ def measure_e2e(spec, args, world=1, rank=0, device="cuda:0"):
                 "encoding": enc, "d2h_gbs_per_gpu": bo * steps / el / 1e9,
                 "note": "in-kernel episode reset on; PCIe-bound: %.1f MB D2H per step per GPU" % (bo / 1e6)})
     del env
+    # (a') Checkers: the same call with the tiles packed 2 bits per cell (cm3_b200/tiles.py decodes on the consumer's side)
+    if spec["kind"] == "checkers":
+        env = VecCheckers(B, device=device, tile_dtype="u2", env_id_offset=rank * B, **spec["ctor"])
+        env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
+        env.rollout_host(a)
+        sync_all()
+        t0 = time.perf_counter()
+        for r in range(reps):
+            out = env.rollout_host(a, t0=r * Th)
+        float(out["reward"][-1, 0])
+        el = _max_over_ranks(time.perf_counter() - t0, world, device)
+        bo = sum(v[0].nbytes for v in out.values())
+        res["packed_u2_tiles"] = {"value": world * B * N * steps / el, "unit": UNIT, "d2h_bytes_per_step": world * int(bo),
+                                  "steps": steps, "ms_per_step": el * 1e3 / steps,
+                                  "encoding": "grid / obs_self_t 2 bits per cell in 32-bit words (CM3_TILE_U2, lossless; the consumer decodes), vectors and rewards fp32"}
+        del env
     # (b) round 1's path: step_host, fp32 tiles, copy / kernel / copy in series
     env = make_env(spec, B, device, env_id_offset=rank * B)
     steps = max(3, min(args.e2e_steps, 30))
@@ -768,6 +784,13 @@ def measure_extras(env, spec, args, peak, mode="fused", world=1, rank=0, device=
                                          "note": "one launch = 33 env steps, device Philox actions, in-kernel reset"}
     del out, plan
     torch.cuda.empty_cache()
+    # (1b) Checkers with the lossless compact tile encodings: the same step, 1/4 and 1/16 of the tile bytes
+    if spec["kind"] == "checkers":
+        for tag, td in (("int8", torch.int8), ("u2", "u2")):
+            r = measure_workload(dict(spec, tile_dtype=td), args.workload, B, K, 33, rank, world, device, local_rank, peak,
+                                 modes=("fused",), sample_clocks=False)
+            extra["fused_%s_tiles" % tag] = dict(r["fused"], note="grid / obs_self_t as %s: the roofline fraction is against THIS layout's algorithmic bytes" % (
+                "int8" if tag == "int8" else "2 bits per cell (CM3_TILE_U2)"))
     # (2) the other env family and the other configs named by BASELINE.json, same batch per GPU
     others = [w for w in ("ck2", "pa4", "pa3", "pm2", "ck1") if w != args.workload]
     extra["workloads"] = {}

@@ -8,7 +8,7 @@ MAX_AGENTS = 8
 ABI_VERSION = 2
 MAX_DST = 8
 REAL_F32, REAL_F64 = 0, 1
-TILE_REAL, TILE_I8 = 0, 1
+TILE_REAL, TILE_I8, TILE_U2 = 0, 1, 2
 
 STATUS_NAMES = {0: "CM3_OK", -1: "CM3_ERR_BAD_ARG", -2: "CM3_ERR_BAD_SHAPE", -3: "CM3_ERR_CUDA",
                 -4: "CM3_ERR_UNSUPPORTED", -5: "CM3_ERR_NO_DEVICE", -6: "CM3_ERR_NCCL"}

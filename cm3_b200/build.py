@@ -11,7 +11,8 @@ UNITS = [("api.cu", (), "api"), ("comm.cu", (), "comm"), ("particle.cu", (), "pa
          ("particle_pair.cu", (), "particle_pair"), ("particle_duo.cu", (), "particle_duo"),
          ("checkers.cu", ("CM3_CK_REAL=0",), "checkers_f32"),
          ("checkers.cu", ("CM3_CK_REAL=1",), "checkers_f64"),
-         ("checkers.cu", ("CM3_CK_REAL=2",), "checkers_f32_i8")]
+         ("checkers.cu", ("CM3_CK_REAL=2",), "checkers_f32_i8"),
+         ("checkers.cu", ("CM3_CK_REAL=3",), "checkers_f32_u2")]
 SOURCES = ["api.cu", "comm.cu", "checkers.cu", "particle.cu", "particle_pair.cu", "particle_duo.cu"]
 HEADERS = ["common.cuh", "params.cuh", "particle_math.cuh", os.path.join("..", "..", "include", "cm3env.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -153,7 +153,9 @@ int balance_waves(const void *kern, int threads, int smem, int nblocks) {
             const long waves = (nblocks + resident - 1) / resident;
             const long last = nblocks - (waves - 1) * resident;
             const int target = (int)((nblocks + waves * sms - 1) / (waves * sms));  // blocks per SM of equal waves
-            if (2 * last < resident && target < per_sm) {
+            // rebalance when the last wave would be less than half full (CM3_BALANCE_FRAC overrides the 0.5)
+            static const double frac = [] { const char *v = getenv("CM3_BALANCE_FRAC"); return v ? atof(v) : 0.5; }();
+            if ((double)last < frac * (double)resident && target < per_sm) {
                 // grow the request until the occupancy calculator agrees with the target
                 int lo = smem, hi = std::min(optin, smem_sm / target);
                 for (int s = hi; s >= lo; s -= 1024) {
@@ -344,12 +346,12 @@ int cm3_checkers_create(const cm3_checkers_config *cfg, cm3_checkers_t *out) {
     }
     if (O < 1 || N < 1 || cfg->num_envs < 1 || cfg->max_steps < 0 || cfg->max_steps > 0xFFFFFF ||
         (cfg->real != CM3_REAL_F32 && cfg->real != CM3_REAL_F64) ||
-        (cfg->tile != CM3_TILE_REAL && cfg->tile != CM3_TILE_I8)) {
+        (cfg->tile != CM3_TILE_REAL && cfg->tile != CM3_TILE_I8 && cfg->tile != CM3_TILE_U2)) {
         set_error("bad n_obs/n_agents/num_envs/max_steps/real/tile");
         return CM3_ERR_BAD_ARG;
     }
-    if (cfg->tile == CM3_TILE_I8 && cfg->real != CM3_REAL_F32) {
-        set_error("int8 tiles are compiled for float outputs only");
+    if (cfg->tile != CM3_TILE_REAL && cfg->real != CM3_REAL_F32) {
+        set_error("compact tiles are compiled for float outputs only");
         return CM3_ERR_UNSUPPORTED;
     }
     if (N > CM3_MAX_AGENTS || !checkers_geometry_supported(R, C, O, N)) {
@@ -518,13 +520,17 @@ static int ck_step_host(cm3_checkers_t h, const cm3_checkers_state *st, const in
     const size_t B = h->cfg.num_envs, N = h->cfg.n_agents, rs = real_size(h->cfg.real);
     const size_t W = 2 * h->cfg.n_obs + 1, L = 2 * (N > 1 ? N - 1 : 1);
     const size_t ts = h->cfg.tile == CM3_TILE_I8 ? 1 : rs;
+    const bool u2 = h->cfg.tile == CM3_TILE_U2;
+    // bytes per env of the two tile fields (CM3_TILE_U2: packed rows, see the header)
+    const size_t grid_b = u2 ? (size_t)h->cfg.n_rows * ((h->cfg.n_columns + 1 + 7) / 8) * 4 : (size_t)h->cfg.n_rows * (h->cfg.n_columns + 1) * 2 * ts;
+    const size_t win_b = u2 ? W * ((6 * W + 31) / 32) * 4 : W * W * 3 * ts;
     static const cm3_checkers_outputs none = {};
     if (!oh) oh = &none;
     const FieldCopy cp[] = {
-        {oh->grid, od->grid, B * h->cfg.n_rows * (h->cfg.n_columns + 1) * 2 * ts},
+        {oh->grid, od->grid, B * grid_b},
         {oh->vec, od->vec, B * N * 4 * rs},
         {oh->obs_others, od->obs_others, B * N * L * rs},
-        {oh->obs_self_t, od->obs_self_t, B * N * W * W * 3 * ts},
+        {oh->obs_self_t, od->obs_self_t, B * N * win_b},
         {oh->obs_self_v, od->obs_self_v, B * N * 4 * rs},
         {oh->reward, od->reward, B * rs},
         {oh->local_rewards, od->local_rewards, B * N * rs},

@@ -25,7 +25,7 @@
 #include "params.cuh"
 
 #ifndef CM3_CK_REAL
-#error "compile with -DCM3_CK_REAL=0 (float), =1 (double) and =2 (float + int8 tiles)"
+#error "compile with -DCM3_CK_REAL=0 (float), =1 (double), =2 (float + int8 tiles) and =3 (float + 2-bit packed tiles)"
 #endif
 
 namespace cm3 {
@@ -56,6 +56,29 @@ template <> __device__ __forceinline__ double tri_cell<double>(uint32_t w, int j
 }
 template <> __device__ __forceinline__ int8_t tri_cell<int8_t>(uint32_t w, int j) {
     return (int8_t)(((w >> j) & 1u) | (((w >> (j + 8)) & 1u) * 0xFEu));
+}
+
+// CM3_TILE_U2: the two bulky outputs as 2 bits per cell (0 -> 0, 1 -> +1, 3 -> -1: two's complement),
+// least significant cell first, packed into 32-bit words:
+//   obs_self_t [B][N][W][RW]   one window ROW (W cells x 3 channels, cell (dc, ch) at bits 2 (3 dc + ch))
+//                              per RW = ceil(6 W / 32) words: one word for n_obs <= 2, two for n_obs = 3
+//   grid       [B][R][GW]      one grid ROW (C + 1 cells x 2 channels, cell (j, ch) at bits 2 (2 j + ch)),
+//                              8 cells per word, GW = ceil((C + 1) / 8) words
+// The same numbers in 1/16 of the float bytes (CK2: 816 -> 64 bytes of tiles per env-step).
+struct TileU2 { uint32_t w; };
+template <typename Tile> struct is_u2 { static constexpr bool value = false; };
+template <> struct is_u2<TileU2> { static constexpr bool value = true; };
+__host__ __device__ constexpr int u2_row_words(int W) { return (6 * W + 31) / 32; }
+__host__ __device__ constexpr int u2_grid_words(int C) { return (C + 1 + 7) / 8; }
+// bit i of x (i < 5) -> bit 6 i: the 25 partial products of the multiplication land on distinct bit
+// positions (i + 5 k = i' + 5 k' with |i - i'| <= 4 forces equality), so there are no carries
+__device__ __forceinline__ uint32_t u2_spread6(uint32_t x5) { return (x5 * 0x00108421u) & 0x01041041u; }
+// bit i of x (i < 8) -> bit 4 i
+__device__ __forceinline__ uint32_t u2_spread4(uint32_t x) {
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x;
 }
 
 template <typename Real> __device__ __forceinline__ void store4(Real *p, Real a, Real b, Real c, Real d);
@@ -131,12 +154,19 @@ struct CkLayout {
     static constexpr int L = 2 * (N > 1 ? N - 1 : 1);
     static constexpr int NP = ck_lanes_per_env(N);
     static constexpr int EW = kWarp / NP;  // envs per warp
-    template <class Geo> __host__ __device__ static int win_bytes(const Geo &g) {
+    // elements of Tile per agent window / per env grid
+    template <class Geo> __host__ __device__ static int win_elems(const Geo &g) {
         const int W = 2 * g.O() + 1;
-        return round_up(EW * N * W * W * 3 * (int)sizeof(Tile), 16);
+        return is_u2<Tile>::value ? W * u2_row_words(W) : W * W * 3;
+    }
+    template <class Geo> __host__ __device__ static int grid_elems(const Geo &g) {
+        return is_u2<Tile>::value ? g.R() * u2_grid_words(g.C()) : g.R() * (g.C() + 1) * 2;
+    }
+    template <class Geo> __host__ __device__ static int win_bytes(const Geo &g) {
+        return round_up(EW * N * win_elems(g) * (int)sizeof(Tile), 16);
     }
     template <class Geo> __host__ __device__ static int grid_bytes(const Geo &g) {
-        return round_up(EW * g.R() * (g.C() + 1) * 2 * (int)sizeof(Tile), 16);
+        return round_up(EW * grid_elems(g) * (int)sizeof(Tile), 16);
     }
     template <class Geo> __host__ __device__ static int lut_bytes(const Geo &g) {
         const int TR = g.R() + 2 * g.O(), TC = g.C() + 2 * g.O() + 1, CNT = g.R() * g.C() / 2 + 1;
@@ -159,7 +189,8 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     using Ly = CkLayout<N, Real, Tile>;
     const Geo geo(p);
     const int R = geo.R(), C = geo.C(), O = geo.O();
-    const int TR = R + 2 * O, TC = C + 2 * O + 1, W = 2 * O + 1, WW3 = W * W * 3, G = R * (C + 1) * 2;
+    const int TR = R + 2 * O, TC = C + 2 * O + 1, W = 2 * O + 1;
+    const int WW3 = Ly::win_elems(geo), G = Ly::grid_elems(geo);  // Tile elements per agent window / per env grid
     const int CNT = R * C / 2 + 1;
     constexpr int L = Ly::L, EW = Ly::EW;
     const uint32_t CM = (C >= 32) ? 0xFFFFFFFFu : ((1u << C) - 1u);
@@ -273,13 +304,31 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 const uint32_t ng1 = ((rowrem & omask) << O) >> sh;
                 const uint32_t nz2 = (border | occ) >> sh;
                 const uint32_t ng2 = occ >> sh;
-                const uint32_t w0 = tri_pack(nz0, ng0), w1 = tri_pack(nz1, ng1), w2 = tri_pack(nz2, ng2);
+                if constexpr (is_u2<Tile>::value) {
+                    // one packed word (two for n_obs = 3) per window row
+                    const uint32_t wm = (1u << W) - 1u;
+                    uint32_t *row = reinterpret_cast<uint32_t *>(win) + dr * u2_row_words(W);
+                    if (W <= 5) {
+                        row[0] = u2_spread6(nz0 & wm) | (u2_spread6(ng0 & wm) << 1) | (u2_spread6(nz1 & wm) << 2) |
+                                 (u2_spread6(ng1 & wm) << 3) | (u2_spread6(nz2 & wm) << 4) | (u2_spread6(ng2 & wm) << 5);
+                    } else {
+                        unsigned long long acc = 0ull;
+                        for (int dc = 0; dc < W; ++dc) {
+                            const unsigned long long code = ((nz0 >> dc) & 1u) | (((ng0 >> dc) & 1u) << 1) | (((nz1 >> dc) & 1u) << 2) |
+                                                            (((ng1 >> dc) & 1u) << 3) | (((nz2 >> dc) & 1u) << 4) | (((ng2 >> dc) & 1u) << 5);
+                            acc |= code << (6 * dc);
+                        }
+                        row[0] = (uint32_t)acc; row[1] = (uint32_t)(acc >> 32);
+                    }
+                } else {
+                    const uint32_t w0 = tri_pack(nz0, ng0), w1 = tri_pack(nz1, ng1), w2 = tri_pack(nz2, ng2);
 #pragma unroll
-                for (int dc = 0; dc < W; ++dc) {
-                    Tile *cell = win + (dr * W + dc) * 3;
-                    cell[0] = tri_cell<Tile>(w0, dc);
-                    cell[1] = tri_cell<Tile>(w1, dc);
-                    cell[2] = tri_cell<Tile>(w2, dc);
+                    for (int dc = 0; dc < W; ++dc) {
+                        Tile *cell = win + (dr * W + dc) * 3;
+                        cell[0] = tri_cell<Tile>(w0, dc);
+                        cell[1] = tri_cell<Tile>(w1, dc);
+                        cell[2] = tri_cell<Tile>(w2, dc);
+                    }
                 }
             }
         }
@@ -306,6 +355,22 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         }
         // ---------------- global grid (get_valid_grid, :66-76).  N > 1: lane a < 2 writes channel a;
         // N == 1: the env's second lane writes both channels
+        if constexpr (is_u2<Tile>::value) {
+            // packed grid rows: N > 1 - lane a < 2 takes the rows i with (i & 1) == a; N == 1 - the second lane takes all
+            if (o0.grid != nullptr && live && (N == 1 ? a == 1 : a < 2)) {
+                uint32_t *gr = reinterpret_cast<uint32_t *>(stage_grid) + e * G;
+                const int GW = u2_grid_words(C);
+                for (int i = (N == 1 ? 0 : a); i < R; i += (N == 1 ? 1 : 2)) {
+                    const uint32_t rowrem = (uint32_t)(rem >> (i * C)) & CM;
+                    const uint32_t c0 = (i & 1) ? kOdd : kEven, c1 = (i & 1) ? kEven : kOdd;  // channel 0 green, 1 orange
+                    for (int gw = 0; gw < GW; ++gw) {
+                        const int j0 = 8 * gw;
+                        gr[i * GW + gw] = u2_spread4((c0 >> j0) & 0xFFu) | (u2_spread4(((rowrem & c0) >> j0) & 0xFFu) << 1) |
+                                          (u2_spread4((c1 >> j0) & 0xFFu) << 2) | (u2_spread4(((rowrem & c1) >> j0) & 0xFFu) << 3);
+                    }
+                }
+            }
+        } else
         if (o0.grid != nullptr && live && (N == 1 ? a == 1 : a < 2)) {
             Tile *gr = stage_grid + e * G;
 #pragma unroll
@@ -582,12 +647,12 @@ int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStrea
 }
 
 int checkers_launch(int R, int C, int O, int N, int real, int tile, const CkParams &p, cudaStream_t stream) {
-    if (tile == CM3_TILE_I8) {
+    if (tile == CM3_TILE_I8 || tile == CM3_TILE_U2) {
         if (real != CM3_REAL_F32) {
-            set_error("int8 tiles are compiled for float outputs only");
+            set_error("compact tiles are compiled for float outputs only");
             return CM3_ERR_UNSUPPORTED;
         }
-        return checkers_launch_f32_i8(R, C, O, N, p, stream);
+        return tile == CM3_TILE_I8 ? checkers_launch_f32_i8(R, C, O, N, p, stream) : checkers_launch_f32_u2(R, C, O, N, p, stream);
     }
     if (real == CM3_REAL_F64) return checkers_launch_f64(R, C, O, N, p, stream);
     return checkers_launch_f32(R, C, O, N, p, stream);
@@ -596,9 +661,13 @@ int checkers_launch(int R, int C, int O, int N, int real, int tile, const CkPara
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
     return dispatch_ck<double, double>(R, C, O, N, p, stream);
 }
-#else
+#elif CM3_CK_REAL == 2
 int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
     return dispatch_ck<float, int8_t>(R, C, O, N, p, stream);
+}
+#else
+int checkers_launch_f32_u2(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream) {
+    return dispatch_ck<float, TileU2>(R, C, O, N, p, stream);
 }
 #endif
 

@@ -99,6 +99,7 @@ int checkers_tile_envs(int N);  // envs per warp tile of the Checkers kernels
 bool dyn_geometry_forced();    // CM3_CK_DYNAMIC=1: always take the geometry-as-data kernels (tests)
 int checkers_launch(int R, int C, int O, int N, int real, int tile, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f32_i8(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
+int checkers_launch_f32_u2(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f32(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int checkers_launch_f64(int R, int C, int O, int N, const CkParams &p, cudaStream_t stream);
 int particle_launch(int N, int real, const PtParams &p, cudaStream_t stream);

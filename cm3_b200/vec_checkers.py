@@ -32,10 +32,16 @@ class VecCheckers(object):
         assert n_columns % 2 == 0
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("dtype must be torch.float32 or torch.float64")
-        # grid / obs_self_t only hold {-1, 0, +1}: tile_dtype=torch.int8 writes them as bytes
+        # grid / obs_self_t only hold {-1, 0, +1}: tile_dtype=torch.int8 writes them as bytes,
+        # tile_dtype="u2" as 2 bits per cell packed in 32-bit words (cm3_b200/tiles.py decodes)
+        self.tile_u2 = isinstance(tile_dtype, str) and tile_dtype == "u2"
+        if self.tile_u2:
+            tile_dtype = torch.int32
+            if dtype != torch.float32:
+                raise ValueError('tile_dtype="u2" needs dtype=torch.float32')
         tile_dtype = dtype if tile_dtype is None else tile_dtype
-        if tile_dtype not in (dtype, torch.int8):
-            raise ValueError("tile_dtype must be None (= dtype) or torch.int8")
+        if tile_dtype not in (dtype, torch.int8) and not self.tile_u2:
+            raise ValueError('tile_dtype must be None (= dtype), torch.int8 or "u2"')
         self.tile_dtype = tile_dtype
         self.lib = L.load_library()
         self.device = torch.device(device)
@@ -63,7 +69,7 @@ class VecCheckers(object):
             cfg.agents_c[i] = int(agents_c[i])
         cfg.num_envs = self.B
         cfg.real = L.REAL_F64 if dtype == torch.float64 else L.REAL_F32
-        cfg.tile = L.TILE_I8 if tile_dtype == torch.int8 and dtype != torch.int8 else L.TILE_REAL
+        cfg.tile = L.TILE_U2 if self.tile_u2 else L.TILE_I8 if tile_dtype == torch.int8 and dtype != torch.int8 else L.TILE_REAL
         cfg.device = dev_index
         cfg.env_id_offset = int(env_id_offset)
         self.env_id_offset = int(env_id_offset)
@@ -97,8 +103,11 @@ class VecCheckers(object):
     # ------------------------------------------------------------------ buffers
     def field_shapes(self):
         B, N, W = self.B, self.N, self.W
-        return dict(grid=(B, self.n_rows, self.n_columns + 1, 2), vec=(B, N, 4),
-                    obs_others=(B, N, self.L_others), obs_self_t=(B, N, W, W, 3),
+        grid, win = (B, self.n_rows, self.n_columns + 1, 2), (B, N, W, W, 3)
+        if self.tile_u2:   # packed rows (include/cm3env.h: CM3_TILE_U2)
+            grid, win = (B, self.n_rows, (self.n_columns + 1 + 7) // 8), (B, N, W, (6 * W + 31) // 32)
+        return dict(grid=grid, vec=(B, N, 4),
+                    obs_others=(B, N, self.L_others), obs_self_t=win,
                     obs_self_v=(B, N, 4), reward=(B,), local_rewards=(B, N), done=(B,), goal_idx=(B, N))
 
     def bytes_per_env_step(self, fields=None):

@@ -54,7 +54,14 @@ typedef enum { CM3_REAL_F32 = 0, CM3_REAL_F64 = 1 } cm3_real;
 /* Element type of the two bulky Checkers outputs (grid, obs_self_t), whose values are always in
  * {-1, 0, +1}: CM3_TILE_REAL writes them as Real like the reference's float arrays, CM3_TILE_I8
  * as signed bytes - the same numbers in a quarter of the bytes (HBM, NVLink and PCIe traffic). */
-typedef enum { CM3_TILE_REAL = 0, CM3_TILE_I8 = 1 } cm3_tile;
+/* CM3_TILE_U2 packs them 2 bits per cell (0 -> 0, 1 -> +1, 3 -> -1), least significant cell first, in
+ * 32-bit words - 1/16 of the float bytes:
+ *   obs_self_t [B][N][W][RW] uint32   one window row (cell (dc, ch) at bits 2 (3 dc + ch)) per
+ *                                     RW = ceil(6 W / 32) words, W = 2 n_obs + 1
+ *   grid       [B][R][GW]    uint32   one grid row (cell (j, ch) at bits 2 (2 j + ch)), 8 cells per word,
+ *                                     GW = ceil((n_columns + 1) / 8)
+ * (cm3_b200/tiles.py holds the decoders.) */
+typedef enum { CM3_TILE_REAL = 0, CM3_TILE_I8 = 1, CM3_TILE_U2 = 2 } cm3_tile;
 
 int cm3_abi_version(void);
 const char *cm3_last_error(void);
@@ -79,7 +86,7 @@ typedef struct {
     int32_t num_envs;      /* B on this device */
     int32_t real;          /* cm3_real of the float outputs */
     int32_t device;        /* CUDA ordinal */
-    int32_t tile;          /* cm3_tile of grid / obs_self_t (CM3_TILE_I8 needs real == F32) */
+    int32_t tile;          /* cm3_tile of grid / obs_self_t (CM3_TILE_I8 / CM3_TILE_U2 need real == F32) */
     int64_t env_id_offset; /* global id of local env 0 (keys the Philox streams, so results
                               do not depend on how the batch is sharded over GPUs) */
     int32_t random_goal;   /* n_agents == 1 only: 1 = an in-kernel episode reset (auto_reset) draws

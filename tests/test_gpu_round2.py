@@ -537,3 +537,59 @@ def test_chained_step_graph_replays_continue_the_trajectory(game):
             assert torch.equal(got[f], want[f]), (game, rep, f)
     with pytest.raises(ValueError):
         ChainedStepGraph(a, acts[:1].contiguous(), a.alloc_outputs(1, fields=fields))
+
+
+# ---------------------------------------------------------------------------------- 2-bit packed tiles
+def _u2_equal_f32(u2env, out_u2, out_f32, msg):
+    from cm3_b200.tiles import unpack_grid_u2, unpack_window_u2
+    for f in gu.CHECKERS_FIELDS:
+        got, want = out_u2[f], out_f32[f]
+        if f == "grid":
+            got = unpack_grid_u2(got, u2env.n_columns).to(torch.float32) if torch.is_tensor(got) else unpack_grid_u2(got, u2env.n_columns).astype(np.float32)
+        elif f == "obs_self_t":
+            got = unpack_window_u2(got, u2env.n_obs).to(torch.float32) if torch.is_tensor(got) else unpack_window_u2(got, u2env.n_obs).astype(np.float32)
+        a = got.cpu().numpy() if torch.is_tensor(got) else got
+        b = want.cpu().numpy() if torch.is_tensor(want) else want
+        np.testing.assert_array_equal(a, b, err_msg="%s %s" % (msg, f))
+
+
+@pytest.mark.parametrize("B", [16, 1000, 4099])
+def test_u2_tiles_are_the_same_numbers(B):
+    """tile_dtype="u2": grid / obs_self_t as 2 bits per cell (CM3_TILE_U2) decode to exactly the float
+    tiles (and hence to the reference), through step, fused rollout and the host-buffer calls."""
+    rng = np.random.default_rng(B)
+    T = 40
+    actions = rng.integers(0, 5, size=(T, B, 2)).astype(np.int8)
+    f32, u2 = VecCheckers(B, **CK2), VecCheckers(B, tile_dtype="u2", **CK2)
+    assert u2.out["grid"].shape == (B, 3, 2) and u2.out["obs_self_t"].shape == (B, 2, 5, 1)
+    assert u2.bytes_per_env_step() == 24 + 40 + 4 * 23 + 1 + 40 + 2
+    a, b = f32.reset(goals=np.eye(2)), u2.reset(goals=np.eye(2))
+    for t in range(T):
+        _u2_equal_f32(u2, b, a, "t=%d" % t)
+        a, b = f32.step(actions[t]), u2.step(actions[t])
+    f32.reset(goals=np.eye(2)); u2.reset(goals=np.eye(2))
+    ra, rb = f32.rollout(T, actions=actions, auto_reset=True), u2.rollout(T, actions=actions, auto_reset=True)
+    _u2_equal_f32(u2, rb, ra, "rollout")
+    h, d = u2.step_host(actions[0]), f32.step(actions[0])
+    _u2_equal_f32(u2, h, {k: v.cpu().numpy() for k, v in d.items()}, "step_host")
+    if B % 32 == 0:
+        f32.reset(goals=np.eye(2)); u2.reset(goals=np.eye(2))
+        hh = u2.rollout_host(actions[:6], auto_reset=True)
+        dd = f32.rollout(6, actions=actions[:6], auto_reset=True)
+        _u2_equal_f32(u2, hh, {k: v.cpu().numpy() for k, v in dd.items()}, "rollout_host")
+
+
+@pytest.mark.parametrize("geom,N", [((5, 12, 3), 2), ((3, 20, 2), 3), ((3, 8, 2), 1), ((7, 8, 1), 4), ((3, 16, 2), 2)])
+def test_u2_tiles_on_other_boards(geom, N):
+    """Two words per window row (n_obs = 3), three grid words per row (21 columns), one and several agents."""
+    R, Cc, O = geom
+    ctor = dict(n_rows=R, n_columns=Cc, n_obs=O, agents_r=[0, R - 1, R // 2, 1][:N], agents_c=[Cc, Cc, Cc, Cc - 1][:N],
+                n_agents=N, max_steps=25)
+    B, T = 200, 40
+    rng = np.random.default_rng(R + Cc + N)
+    actions = rng.integers(0, 5, size=(T, B, N)).astype(np.int8)
+    gi = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
+    f32, u2 = VecCheckers(B, **ctor), VecCheckers(B, tile_dtype="u2", **ctor)
+    f32.reset(goal_idx=gi); u2.reset(goal_idx=gi)
+    ra, rb = f32.rollout(T, actions=actions, auto_reset=True), u2.rollout(T, actions=actions, auto_reset=True)
+    _u2_equal_f32(u2, rb, ra, str(geom))

@@ -21,11 +21,12 @@ def main():
         e = d.get("e2e")
         if e:
             print("   e2e %.4g (%s B D2H/step, %.1f ms/step)%s" % (e["value"], e.get("d2h_bytes_per_step"), e.get("ms_per_step", 0),
-                  ("  unpipelined fp32 %.4g" % e["unpipelined_fp32"]["value"]) if "unpipelined_fp32" in e else ""))
+                  (("  unpipelined fp32 %.4g" % e["unpipelined_fp32"]["value"]) if "unpipelined_fp32" in e else "") +
+                  (("  packed u2 %.4g" % e["packed_u2_tiles"]["value"]) if "packed_u2_tiles" in e else "")))
         if "cpu_baseline" in d:
             print("   cpu_baseline %.4g (%s cores)" % (d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"]))
         x = d.get("extra", {})
-        for k in ("per_step_launches", "per_step_stream_ordered", "fused_rollout_T33_philox"):
+        for k in ("per_step_launches", "per_step_stream_ordered", "fused_rollout_T33_philox", "fused_int8_tiles", "fused_u2_tiles"):
             if k in x:
                 print("   %-26s %.4g  %.3f us/step  frac %.3f" % (k, x[k]["value"], x[k].get("us_per_step", x[k].get("ms_per_launch", 0) * 1e3 / 33), x[k]["frac"]))
         for wl, w in x.get("workloads", {}).items():
