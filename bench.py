@@ -47,6 +47,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 NVLINK_PEER_GBS = 770.0    # B200_PROFILING.md: measured peer copy, per direction per GPU (900 nominal)
 FUSED_T = int(os.environ.get("CM3_BENCH_FUSED_T", "0"))  # experiment: steps per fused launch in measure_workload (0 = one episode)
 SPIN_CYCLES = 4_000_000    # ~2 ms of device spin queued ahead of a timed region (see timed_steps)
+REWARM = os.environ.get("CM3_BENCH_REWARM", "1") != "0"  # re-issue the warm-up steps behind the spin (timed_steps)
 
 
 def workload_spec(name):
@@ -324,6 +325,11 @@ def timed_steps(runner, K, W, world, device, local_rank, sample_clocks=True):
     if sampler:
         sampler.start()
     torch.cuda._sleep(SPIN_CYCLES)
+    if REWARM:
+        # a few more untimed steps behind the spin: the timed launches then follow a launch of the SAME kernel
+        # on the device (same shared-memory carve-out, warm instruction / constant / descriptor caches), as
+        # every launch of a long run does, instead of following a one-thread spin kernel
+        runner.run(W)
     e0.record()
     runner.run(K)
     e1.record()

@@ -84,6 +84,15 @@ int chain_parts(int ntiles) {
     return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
 }
 
+int chain_early_mode(int dflt) {
+    static const int forced = [] {
+        const char *v = getenv("CM3_CHAIN_EARLY");
+        return v ? atoi(v) : -1;
+    }();
+    const int m = forced >= 0 ? forced : dflt;
+    return m < 0 ? 0 : m > 2 ? 2 : m;
+}
+
 // Off by default: measured slower than one env per thread (profiles/r02k_ab.txt, r02l_ab.txt)
 bool duo_enabled() {
     static const bool on = [] {
@@ -503,6 +512,7 @@ int cm3_checkers_step_chained(cm3_checkers_t h, const cm3_checkers_state *st, co
     if (!st->sync) { set_error("step_chained needs state.sync (the per-tile chaining words)"); return CM3_ERR_BAD_ARG; }
     if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = 1; p.auto_reset = auto_reset ? 1 : 0; p.chained = 1;
+    p.early = chain_early_mode(h->cfg.n_agents == 1 ? 2 : 0);  // measured, profiles/r02p_ab.txt
     p.actions = actions; p.seed = seed; p.t0 = t0;
     return ck_launch(h, p, stream);
 }
@@ -782,6 +792,7 @@ int cm3_particle_step_chained(cm3_particle_t h, const cm3_particle_state *st, co
     if (!st->sync) { set_error("step_chained needs state.sync (the per-tile chaining words)"); return CM3_ERR_BAD_ARG; }
     if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = 1; p.auto_reset = auto_reset ? 1 : 0; p.chained = 1;
+    p.early = chain_early_mode(2);  // measured, profiles/r02p_ab.txt
     p.actions = actions; p.seed = seed; p.t0 = t0;
     return pt_launch(h, p, stream);
 }

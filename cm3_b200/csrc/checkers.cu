@@ -441,6 +441,18 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         }
     };
 
+    // ---- store compact state
+    auto store_state = [&]() {
+        if (live && a == 0) {
+            p.remaining[env] = rem;
+            p.meta[env] = (uint32_t)steps | (goals << 24);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                p.agents[(size_t)env * N + i] =
+                    (uint32_t)ar[i] | ((uint32_t)ac[i] << 8) | ((uint32_t)ng[i] << 16) | ((uint32_t)no[i] << 24);
+        }
+    };
+
     const int T_eff = (p.mode == kCkReset) ? 1 : p.T;
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
@@ -544,20 +556,19 @@ checkers_kernel(const __grid_constant__ CkParams p) {
                 reset_state();
             }
         }
+        // The state is final here: the next launch of this tile needs IT, not the observations.  p.early (chained
+        // launches, params.cuh: chain_early_mode) writes it back - and, at 2, releases the tile - before the
+        // tiles of the last step are expanded and stored.
+        if (p.early != 0 && t == T_eff - 1) {
+            store_state();
+            if (p.early == 2) ticket.publish(lane);
+        }
         emit(t);
         if (sel && a == 0 && o0.done != nullptr) o0.done[oe0 + env] = 0;  // checkers.py:291
     }
 
-    // ---- store compact state
-    if (live && a == 0) {
-        p.remaining[env] = rem;
-        p.meta[env] = (uint32_t)steps | (goals << 24);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            p.agents[(size_t)env * N + i] =
-                (uint32_t)ar[i] | ((uint32_t)ac[i] << 8) | ((uint32_t)ng[i] << 16) | ((uint32_t)no[i] << 24);
-    }
-    ticket.publish(lane);  // this tile's next launch may go ahead
+    if (p.early == 0 || T_eff < 1) store_state();
+    if (p.early != 2 || T_eff < 1) ticket.publish(lane);  // this tile's next launch may go ahead
     // smem must outlive the async reads; the global writes themselves complete with the grid
     if (pending && leader) bulk_wait_read();
 }

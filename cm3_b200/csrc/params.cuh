@@ -45,6 +45,9 @@ struct CkParams {
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
     int chained;      // 1: wait for this tile's predecessor only (TileTicket) instead of griddepcontrol.wait
+    int early;        // when the compact state of the launch's LAST step is written back and the tile published
+                      // (params.cuh: chain_early_mode): 0 after the step's outputs, 1 state before / publish after,
+                      // 2 both before the outputs are assembled
     int tile0;        // first tile of this launch (a chained step is issued as several partial grids)
     int random_goal;  // N == 1: in-kernel resets redraw the goal (train_offpolicy.py:291-296)
     int R, C, O;      // board geometry for the kernels that take it as data (checkers.cu: DynGeo)
@@ -80,7 +83,7 @@ struct PtParams {
     int n_dst;
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
-    int chained, tile0;  // see CkParams
+    int chained, tile0, early;  // see CkParams
     unsigned long long seed;
     long long t0, env_id_offset, reset_counter;
     double dt, damping, contact_force, contact_margin, dist_min, mass, sensitivity, reach_thresh;
@@ -119,5 +122,15 @@ bool pdl_enabled();  // programmatic dependent launch between consecutive step l
 // slower for every workload at 2, 3 and 4 parts (profiles/r02c_ab.txt: the extra launches cost more
 // than the overlap returns); CM3_CHAIN_PARTS=<n> re-enables it.
 int chain_parts(int ntiles);
+// Where a chained launch writes its compact state back and publishes its tile (CkParams::early).  The next
+// step's block of the same tile needs the state, not the outputs: storing the state and releasing the
+// ticket BEFORE the observation tiles are assembled and stored takes the whole output phase - and the
+// memory barrier of the release, which otherwise queues behind this block's own tile stores - off the
+// tile-to-tile dependency chain.  Measured at 65 536 envs (profiles/r02p_ab.txt), early = 2 against 0:
+// PA4 0.755 -> 0.778, PA3 0.687 -> 0.745, PM2 0.487 -> 0.54, CK1 0.681 -> 0.691, CK2 0.896 -> 0.878 (its
+// 1.7 waves per launch pipeline without it, and the early barrier only delays the tile stores); early = 1
+// (state before, publish after) is within noise of 0.  Defaults: 2 for the particle kernels and one-agent
+// Checkers, 0 for Checkers with several agents; CM3_CHAIN_EARLY=0|1|2 overrides.
+int chain_early_mode(int dflt);
 
 }  // namespace cm3

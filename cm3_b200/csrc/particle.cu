@@ -285,6 +285,23 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
         if (acts.on) act_word = acts.hand_over(t, act_loaded, lane);
     };
 
+    // compact state back to HBM
+    auto store_state = [&]() {
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                st4<Real>(reinterpret_cast<Real *>(p.sv) + ((size_t)env * N + i) * 4, vx[i], vy[i], px[i], py[i]);
+                if (reset_mode || p.auto_reset) {  // landmarks only change on a reset
+                    Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + i) * 2;
+                    lm[0] = lx[i]; lm[1] = ly[i];
+                }
+            }
+            p.steps[env] = steps;
+            p.collisions[env] = collisions;
+            p.reached[env] = (uint8_t)reached;
+        }
+    };
+
     const int T_eff = reset_mode ? 1 : p.T;
     for (int t = 0; t < T_eff; ++t) {
         bool sel = false;
@@ -457,24 +474,19 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
             rn_ptr += OB * N; rw_ptr += OB; dn_ptr += OB; cl_ptr += OB; rc_ptr += OB;
             if (p.auto_reset && done) reset_state((unsigned long long)(p.t0 + t + 1), kTagAutoReset);
         }
+        // The state is final here: the next launch of this tile needs IT, not the observations.  p.early (chained
+        // launches, params.cuh: chain_early_mode) writes it back - and, at 2, releases the tile - before the
+        // observation tiles of the last step are assembled and stored.
+        if (p.early != 0 && t == T_eff - 1) {
+            store_state();
+            if (p.early == 2) ticket.publish(lane);
+        }
         emit(t);
         if (sel && o0.done != nullptr) o0.done[oe0 + env] = 0;  // np.any(done_n), environment.py:149
     }
 
-    if (valid) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            st4<Real>(reinterpret_cast<Real *>(p.sv) + ((size_t)env * N + i) * 4, vx[i], vy[i], px[i], py[i]);
-            if (reset_mode || p.auto_reset) {  // landmarks only change on a reset
-                Real *lm = reinterpret_cast<Real *>(p.landmarks) + ((size_t)env * N + i) * 2;
-                lm[0] = lx[i]; lm[1] = ly[i];
-            }
-        }
-        p.steps[env] = steps;
-        p.collisions[env] = collisions;
-        p.reached[env] = (uint8_t)reached;
-    }
-    ticket.publish(lane);  // this tile's next launch may go ahead
+    if (p.early == 0 || T_eff < 1) store_state();
+    if (p.early != 2 || T_eff < 1) ticket.publish(lane);  // this tile's next launch may go ahead
     // shared memory must outlive the async reads; the global writes themselves complete with the grid
     if (pending && leader) bulk_wait_read();
 }

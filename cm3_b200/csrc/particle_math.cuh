@@ -38,14 +38,26 @@ template <> __device__ __forceinline__ void st4<double>(double *p, double a, dou
     reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
 }
 
-// np.logaddexp(0, x) - NumPy's npy_logaddexp with x1 = 0 (core.py:192)
+// np.logaddexp(0, x) - NumPy's npy_logaddexp with x1 = 0 (core.py:192):  x == 0 -> 0 + ln 2; tmp = 0 - x; tmp > 0 -> 0 + log1p(exp(-tmp)) = log1p(exp(x));
+// tmp <= 0 -> x + log1p(exp(tmp)); NaN otherwise.  Both branches take log1p(exp(.)) of the same number
+// -|x| (x itself when negative, the exact negation 0 - x when positive), so they are evaluated ONCE and
+// the branch becomes a select: the same bits, but the lanes of a warp whose pairs sit on both sides of
+// contact (x > 0 inside dist_min, x < 0 outside) no longer run two copies of exp + log1p back to back.
 template <typename Real> __device__ __forceinline__ Real logaddexp0(Real x) {
     using Op = RealOps<Real>;
+#ifdef CM3_LAE_BRANCHY  // round 1 / early round 2: the literal three-way branch (A/B builds only)
     if (x == (Real)0) return (Real)0.693147180559945309417232121458176568;
     const Real tmp = Op::sub((Real)0, x);
-    if (tmp > (Real)0) return Op::log1p(Op::exp(x));          // 0 + log1p(exp(-tmp))
+    if (tmp > (Real)0) return Op::log1p(Op::exp(x));
     else if (tmp <= (Real)0) return Op::add(x, Op::log1p(Op::exp(tmp)));
-    return tmp;  // NaN
+    return tmp;
+#else
+    const bool pos = x > (Real)0;
+    const Real e = pos ? Op::sub((Real)0, x) : x;   // -|x| (NaN stays NaN)
+    const Real l = Op::log1p(Op::exp(e));
+    const Real r = pos ? Op::add(x, l) : l;
+    return (x == (Real)0) ? (Real)0.693147180559945309417232121458176568 : r;
+#endif
 }
 
 // Contact geometry of one agent pair (core.py:186-192): delta, dist and the softplus argument
