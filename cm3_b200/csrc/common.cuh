@@ -300,6 +300,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // launch_dependents - i.e. is resident and holds its ticket - so the block a waiter spins on is
 // always running or finished.  The trigger is issued under a branch on the ticket value: the atomic
 // has RETURNED (was performed at L2) before any block of the next grid can take its own ticket.
+// (Measured and dropped, profiles/r02q_ab.txt: issuing the atomic first and consuming its result only
+// after the block's set-up - to hide its round trip - changes nothing; a block that starts late is
+// waiting for a slot, not for its ticket.)
 struct TileTicket {
     uint32_t *w;
     uint32_t mine;
