@@ -581,9 +581,10 @@ def measure_e2e(spec, args, world=1, rank=0, device="cuda:0"):
 
     Headline `value`: VecCheckers/VecParticle.rollout_host -> cm3_*_rollout_host, which double
     buffers the device side (the D2H copy of step t overlaps the kernel of step t + 1), with the
-    lossless compact encoding for Checkers (grid / obs_self_t as int8: their values are always in
-    {-1, 0, +1}).  `unpipelined_fp32` is round 1's call, step_host with fp32 tiles: copy, kernel,
-    copy in series.  With world > 1 every rank drives its own GPU (own PCIe link) at the same
+    most compact lossless encoding for Checkers (grid / obs_self_t, whose values are always in
+    {-1, 0, +1}, packed 2 bits per cell); `int8_tiles` is the same call with one byte per cell in the
+    reference's array shapes; `unpipelined_fp32` is round 1's call, step_host with fp32 tiles: copy,
+    kernel, copy in series.  With world > 1 every rank drives its own GPU (own PCIe link) at the same
     time; values are the whole job's, from the slowest rank."""
     import torch
     import torch.distributed as dist
@@ -599,37 +600,20 @@ def measure_e2e(spec, args, world=1, rank=0, device="cuda:0"):
             dist.barrier()
 
     res = {}
-    # (a) pipelined, compact
-    if spec["kind"] == "checkers":
-        env = VecCheckers(B, device=device, tile_dtype=torch.int8, env_id_offset=rank * B, **spec["ctor"])
-        env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
-        enc = "grid / obs_self_t int8 (lossless: values in {-1,0,+1}), vectors and rewards fp32"
-    else:
-        env = make_env(spec, B, device, env_id_offset=rank * B)
-        enc = "fp32"
-    env.rollout_host(acts)  # warm-up (allocates the pinned areas)
     reps = max(1, min(3, args.e2e_steps // T)) if args.e2e_steps >= T else 1
     Th = T if args.e2e_steps >= T else max(3, args.e2e_steps)
     a = acts[:Th]
-    env.rollout_host(a)
-    sync_all()
-    t0 = time.perf_counter()
-    for r in range(reps):
-        out = env.rollout_host(a, t0=r * Th)
-    float(out["reward"][-1, 0])
-    el = _max_over_ranks(time.perf_counter() - t0, world, device)
-    bo = sum(v[0].nbytes for v in out.values())
     steps = reps * Th
-    res.update({"value": world * B * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": world * B * N,
-                "d2h_bytes_per_step": world * int(bo), "n_gpus": world, "steps": steps, "ms_per_step": el * 1e3 / steps,
-                "api": "Vec*.rollout_host -> cm3_*_rollout_host: per step H2D of the step's actions (pinned), kernel, D2H of every output field (pinned); the D2H of step t overlaps the kernel of step t+1",
-                "encoding": enc, "d2h_gbs_per_gpu": bo * steps / el / 1e9,
-                "note": "in-kernel episode reset on; PCIe-bound: %.1f MB D2H per step per GPU" % (bo / 1e6)})
-    del env
-    # (a') Checkers: the same call with the tiles packed 2 bits per cell (cm3_b200/tiles.py decodes on the consumer's side)
-    if spec["kind"] == "checkers":
-        env = VecCheckers(B, device=device, tile_dtype="u2", env_id_offset=rank * B, **spec["ctor"])
-        env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
+    API = ("Vec*.rollout_host -> cm3_*_rollout_host: per step H2D of the step's actions (pinned), kernel, D2H of every output "
+           "field (pinned); the D2H of step t overlaps the kernel of step t+1")
+
+    def pipelined(tile_dtype, enc):
+        if spec["kind"] == "checkers":
+            env = VecCheckers(B, device=device, tile_dtype=tile_dtype, env_id_offset=rank * B, **spec["ctor"])
+            env.reset(goals=np.eye(2) if spec["n"] == 2 else np.array([[1, 0]]))
+        else:
+            env = make_env(spec, B, device, env_id_offset=rank * B)
+        env.rollout_host(acts)  # warm-up (allocates the pinned areas)
         env.rollout_host(a)
         sync_all()
         t0 = time.perf_counter()
@@ -638,10 +622,21 @@ def measure_e2e(spec, args, world=1, rank=0, device="cuda:0"):
         float(out["reward"][-1, 0])
         el = _max_over_ranks(time.perf_counter() - t0, world, device)
         bo = sum(v[0].nbytes for v in out.values())
-        res["packed_u2_tiles"] = {"value": world * B * N * steps / el, "unit": UNIT, "d2h_bytes_per_step": world * int(bo),
-                                  "steps": steps, "ms_per_step": el * 1e3 / steps,
-                                  "encoding": "grid / obs_self_t 2 bits per cell in 32-bit words (CM3_TILE_U2, lossless; the consumer decodes), vectors and rewards fp32"}
         del env
+        return {"value": world * B * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": world * B * N,
+                "d2h_bytes_per_step": world * int(bo), "n_gpus": world, "steps": steps, "ms_per_step": el * 1e3 / steps,
+                "api": API, "encoding": enc, "d2h_gbs_per_gpu": bo * steps / el / 1e9,
+                "note": "in-kernel episode reset on; PCIe-bound: %.1f MB D2H per step per GPU" % (bo / 1e6)}
+
+    # (a) pipelined, with the most compact lossless encoding the library offers: Checkers packs the two tile
+    # outputs 2 bits per cell (CM3_TILE_U2, include/cm3env.h; cm3_b200/tiles.py decodes); (a') the same with
+    # int8 tiles (arrays of the reference's shapes, one byte per cell).  Particle outputs are fp32 as they are.
+    if spec["kind"] == "checkers":
+        res.update(pipelined("u2", "grid / obs_self_t packed 2 bits per cell in 32-bit words (CM3_TILE_U2: lossless, their values are "
+                                   "always in {-1, 0, +1}; cm3_b200/tiles.py decodes on the consumer's side), vectors and rewards fp32"))
+        res["int8_tiles"] = pipelined(torch.int8, "grid / obs_self_t int8 in the reference's array shapes (lossless), vectors and rewards fp32")
+    else:
+        res.update(pipelined(None, "fp32"))
     # (b) round 1's path: step_host, fp32 tiles, copy / kernel / copy in series
     env = make_env(spec, B, device, env_id_offset=rank * B)
     steps = max(3, min(args.e2e_steps, 30))

@@ -183,6 +183,10 @@ __host__ __device__ constexpr int sw_bits_for(int chunks) {
 }
 __host__ __device__ constexpr int sw_row_bytes(int bits) { return bits ? (16 << bits) : 128; }
 
+#ifndef CM3_PT_STAGE_MAXN
+#define CM3_PT_STAGE_MAXN 2   // largest agent count with a double-buffered staging set; 3 fits as well and was measured
+                              // again in round 2 (profiles/r02r_ab.txt): fused within noise, chained per-step 2 % slower
+#endif
 template <int N, typename Real>
 struct PtGeom {
     static constexpr int NO = (N > 1) ? N - 1 : 1;  // "other" agents per agent
@@ -203,7 +207,7 @@ struct PtGeom {
     // one-wave 65 536-env batch anyway.
     static constexpr int kSetBytes = round_up(kOthOff + kOthBytes, 1024);
     static constexpr int kOverhead = ActionStream<N>::kSmemBytes + 1024 /* alignment slack */;
-    static constexpr int kStages = (N <= 2 && 14 * (2 * kSetBytes + kOverhead + 1024 /* driver-reserved */) <= 227 * 1024) ? 2 : 1;
+    static constexpr int kStages = (N <= CM3_PT_STAGE_MAXN && 14 * (2 * kSetBytes + kOverhead + 1024 /* driver-reserved */) <= 227 * 1024) ? 2 : 1;
     static constexpr int kActOff = kStages * kSetBytes;             // ActionStream slots
     static constexpr int kSmemBytes = kActOff + kOverhead;
     // a TMA box has at most 256 rows: the wide records of N >= 6 (and N = 5..8 in double) do not fit

@@ -22,7 +22,8 @@ def main():
         if e:
             print("   e2e %.4g (%s B D2H/step, %.1f ms/step)%s" % (e["value"], e.get("d2h_bytes_per_step"), e.get("ms_per_step", 0),
                   (("  unpipelined fp32 %.4g" % e["unpipelined_fp32"]["value"]) if "unpipelined_fp32" in e else "") +
-                  (("  packed u2 %.4g" % e["packed_u2_tiles"]["value"]) if "packed_u2_tiles" in e else "")))
+                  (("  packed u2 %.4g" % e["packed_u2_tiles"]["value"]) if "packed_u2_tiles" in e else "") +
+                  (("  int8 tiles %.4g" % e["int8_tiles"]["value"]) if "int8_tiles" in e else "")))
         if "cpu_baseline" in d:
             print("   cpu_baseline %.4g (%s cores)" % (d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"]))
         x = d.get("extra", {})
