@@ -46,7 +46,7 @@ MAX_STEPS = 33      # alg/config.json:61
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 NVLINK_PEER_GBS = 770.0    # B200_PROFILING.md: measured peer copy, per direction per GPU (900 nominal)
 FUSED_T = int(os.environ.get("CM3_BENCH_FUSED_T", "0"))  # experiment: steps per fused launch in measure_workload (0 = one episode)
-SPIN_CYCLES = 4_000_000    # ~2 ms of device spin queued ahead of a timed region (see timed_steps)
+SPIN_CYCLES = int(os.environ.get("CM3_BENCH_SPIN", "4000000"))  # ~2 ms of device spin queued ahead of a timed region (see timed_steps)
 REWARM = os.environ.get("CM3_BENCH_REWARM", "1") != "0"  # re-issue the warm-up steps behind the spin (timed_steps)
 
 
@@ -294,6 +294,15 @@ class FusedRunner(object):
         self.launches += n_full + (1 if rem else 0)
 
 
+def step_ring(bpe, B):
+    """Slots of the rollout ring of the per-step modes = steps per CUDA-graph replay: larger than L2 (at least 33
+    slots and 512 MB of outputs), and up to 264 slots within 4 GB so that one replay is ~1 ms of device work even
+    for the 4 us steps of the small particle envs - the host then never has to issue replays faster than every
+    millisecond (with 39-slot rings the PM2 line read 10 % low whenever the host thread was briefly descheduled)."""
+    per_slot = bpe * B
+    return int(min(4096, max(MAX_STEPS, np.ceil(512e6 / per_slot), min(264, 4e9 // per_slot))))
+
+
 def bytes_per_env_step(env):
     return env.bytes_per_env_step()
 
@@ -427,7 +436,7 @@ def measure_workload(spec, wl, B, K, W, rank, world, device, local_rank, peak, m
                         "us_per_step": ms * 1e3 / Kf, "achieved_gbs": ach, "frac": ach / peak,
                         "algorithmic_bytes_per_env_step": fb, "per_rank_ms": per_rank, "clocks": clocks}
         del runner
-    ring = min(4096, max(T, int(np.ceil(512e6 / (bpe * B)))))
+    ring = step_ring(bpe, B)
     for name, chained in (("per_step_chained", True), ("per_step_stream_ordered", False)):
         if name in modes or "step" in modes:
             runner = StepRunner(env, spec, ring, SEED + rank, chained=chained)
@@ -453,8 +462,7 @@ def run_gpu(args):
     B, K, W = args.envs, args.steps, args.warmup
     env = make_env(spec, B, device, env_id_offset=rank * B)
     bpe = bytes_per_env_step(env)
-    # ring larger than L2 (126 MB): at least 33 slots and >= 512 MB of outputs
-    ring = max(MAX_STEPS, int(np.ceil(512e6 / (bpe * B))))
+    ring = step_ring(bpe, B)
     gather_mode = None
     T = MAX_STEPS
     W = max(W, 3)
