@@ -295,12 +295,11 @@ class FusedRunner(object):
 
 
 def step_ring(bpe, B):
-    """Slots of the rollout ring of the per-step modes = steps per CUDA-graph replay: larger than L2 (at least 33
-    slots and 512 MB of outputs), and up to 264 slots within 4 GB so that one replay is ~1 ms of device work even
-    for the 4 us steps of the small particle envs - the host then never has to issue replays faster than every
-    millisecond (with 39-slot rings the PM2 line read 10 % low whenever the host thread was briefly descheduled)."""
-    per_slot = bpe * B
-    return int(min(4096, max(MAX_STEPS, np.ceil(512e6 / per_slot), min(264, 4e9 // per_slot))))
+    """Slots of the rollout ring of the per-step modes (= steps per CUDA-graph replay): larger than L2 - at least 33
+    slots and 512 MB of outputs.  (Longer rings were tried so that one replay is ~1 ms of device work even for the
+    4 us steps of the small particle envs: the PM2 line got SLOWER with the ring, 3.95 -> 4.4 -> 4.9 us per step at
+    39 / 66 / 132+ slots, tools/exp_pm2_step.py; the host is not what limits it.)"""
+    return int(min(4096, max(MAX_STEPS, np.ceil(512e6 / (bpe * B)))))
 
 
 def bytes_per_env_step(env):
