@@ -47,6 +47,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 NVLINK_PEER_GBS = 770.0    # B200_PROFILING.md: measured peer copy, per direction per GPU (900 nominal)
 FUSED_T = int(os.environ.get("CM3_BENCH_FUSED_T", "0"))  # experiment: steps per fused launch in measure_workload (0 = one episode)
 SPIN_CYCLES = int(os.environ.get("CM3_BENCH_SPIN", "4000000"))  # ~2 ms of device spin queued ahead of a timed region (see timed_steps)
+NUMA_CPUS = 0  # CPUs this process was bound to (cm3_b200.sharding.bind_host_to_gpu), 0 = not bound
 REWARM = os.environ.get("CM3_BENCH_REWARM", "1") != "0"  # re-issue the warm-up steps behind the spin (timed_steps)
 
 
@@ -388,6 +389,9 @@ def setup_dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from cm3_b200.sharding import bind_host_to_gpu
+    global NUMA_CPUS
+    NUMA_CPUS = bind_host_to_gpu(local_rank)   # pinned host buffers of the e2e path on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: whatever NCCL prints while the communicator comes up
@@ -513,7 +517,8 @@ def run_gpu(args):
     config = workload_config(spec, B, launch_cfg.pop("l2"))
     launch_config = dict({"mode": mode, "actions": "int8 in HBM", "auto_reset": "in-kernel",
                           "parallelism": "env batch sharded over %d GPU(s), no per-step collective" % world,
-                          "timing": "CUDA events on the launching stream behind a %d-cycle device spin (all launches enqueued before the first event fires); barrier + synchronize both sides; max over ranks" % SPIN_CYCLES},
+                          "timing": "CUDA events on the launching stream behind a %d-cycle device spin (all launches enqueued before the first event fires); barrier + synchronize both sides; max over ranks" % SPIN_CYCLES,
+                          "host_affinity": ("each rank bound to the %d CPUs next to its GPU (NVML affinity mask)" % NUMA_CPUS) if NUMA_CPUS else "not bound"},
                          **launch_cfg)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

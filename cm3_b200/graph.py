@@ -19,8 +19,8 @@ class ChainedStepGraph(object):
         if actions.dtype != torch.int8 or tuple(actions.shape) != (ring, env.B, env.N) or not actions.is_contiguous() \
                 or actions.device != env.device:
             raise ValueError("actions must be a contiguous int8 device tensor [ring, B, N]")
-        if ring < 2:
-            raise ValueError("a chained launch must not write the previous launch's slot: ring >= 2")
+        if ring < 3:
+            raise ValueError("a chained launch must not write the slots of the previous two launches: ring >= 3")
         for k, v in out_ring.items():
             if int(v.shape[0]) != ring or int(v.shape[1]) != env.B:
                 raise ValueError("out_ring[%r] must be [ring, B, ...]" % k)

@@ -30,6 +30,37 @@ def split_envs(total_envs, world):
     return out
 
 
+def bind_host_to_gpu(local_rank):
+    """Pins the calling process to the CPU cores next to GPU `local_rank` (NVML's ideal affinity mask), so that the
+    pinned host buffers it allocates afterwards - and the thread that drives the GPU - sit on that GPU's NUMA node.
+    One process per GPU with host-buffer I/O (cm3_*_rollout_host) otherwise lands on whichever socket the launcher
+    picked and may copy across the socket link.  Returns the number of CPUs bound to, or 0 when NVML is unavailable
+    (nothing is changed then).  CM3_BIND_NUMA=0 disables.  On the single-socket hosts of this pool the mask is
+    every CPU and the call changes nothing (measured: e2e 51-52 GB/s either way); it is there for multi-socket hosts."""
+    if os.environ.get("CM3_BIND_NUMA", "1") == "0":
+        return 0
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = local_rank
+        if vis:
+            ids = vis.split(",")
+            if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+                phys = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))   # never widen what the launcher / container allows
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001 - an optimisation, never a requirement
+        return 0
+
+
 class EnvShard(object):
     """The env-id range owned by this rank.  rank / world default to the initialised process
     group, else to torchrun's RANK / WORLD_SIZE, else to a single process."""

@@ -215,7 +215,7 @@ class VecCheckers(object):
         """One step that may overlap the previous launch on the device (cm3_checkers_step_chained):
         `actions` is an int8 device tensor [B,N] that was complete before the previous call was
         made (a slice of a pre-generated stream), `out` a dict of [B,...] (or [1,B,...]) buffers
-        that is not the previous call's - a slot of a rollout ring."""
+        that is not one of the previous two calls' - a slot of a rollout ring of at least three."""
         oc = out if isinstance(out, L.CheckersOutputs) else self._outputs_struct(out)
         L.check(self.lib.cm3_checkers_step_chained(self._h, C.byref(self._st), _ptr(actions), int(seed) & (2**64 - 1),
                                                    int(t0), 1 if auto_reset else 0, C.byref(oc), self._stream()))

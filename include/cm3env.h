@@ -177,7 +177,10 @@ int cm3_checkers_rollout(cm3_checkers_t h, const cm3_checkers_state *st, const i
  * Contract: (1) st->sync non-NULL; (2) `actions` was complete in memory before the PREVIOUS launch
  * on this stream was enqueued, or is written by a kernel that sits between the two step launches
  * in the stream (that kernel then orders everything, as usual); (3) `outs` does not alias the
- * previous launch's outs (use a ring of >= 2 slots).  auto_reset as in cm3_checkers_rollout
+ * outs of the previous TWO launches (use a ring of >= 3 slots): a launch releases its tile as soon
+ * as the compact state is stored, possibly before its own outputs have left the SM, so the next
+ * launch's outputs - and the one after that, which only waits for the next launch's state - may
+ * be on their way at the same time.  auto_reset as in cm3_checkers_rollout
  * (seed / t0 key the goal redraw when cfg.random_goal is set). */
 int cm3_checkers_step_chained(cm3_checkers_t h, const cm3_checkers_state *st, const int8_t *actions,
                               uint64_t seed, int64_t t0, int32_t auto_reset,
