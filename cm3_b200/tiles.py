@@ -9,7 +9,7 @@ reference's arrays; they work on NumPy arrays and on torch tensors (any device) 
 import numpy as np
 
 
-def _codes(words, n_cells, xp, is_torch):
+def _codes(words, n_cells, is_torch):
     """words [..., nw] (32-bit) -> values [..., n_cells] in {-1, 0, 1} (int8), cell k at bits 2 k."""
     if is_torch:
         import torch
@@ -32,7 +32,7 @@ def unpack_window_u2(words, n_obs):
     """obs_self_t words [..., W, RW] -> [..., W, W, 3] int8 (W = 2 n_obs + 1)."""
     W = 2 * n_obs + 1
     t = _is_torch(words)
-    vals = _codes(words, 3 * W, np, t)            # [..., W, 3 W]: one row's cells in (dc, ch) order
+    vals = _codes(words, 3 * W, t)            # [..., W, 3 W]: one row's cells in (dc, ch) order
     return vals.reshape(tuple(vals.shape[:-1]) + (W, 3))
 
 
