@@ -8,7 +8,9 @@ TEST INFRASTRUCTURE ONLY.  Executes, from /root/reference (nothing is edited or 
     fields) and alg/train_onpolicy.py:329-338 (particle, 11 fields) assemble them;
   * alg/replay_buffer.py Replay_Buffer.add / sample_batch (ring of transitions);
   * alg/alg_credit_checkers.py Alg.process_batch / process_actions (:378-477) and
-    alg/alg_credit.py Alg.process_batch / process_actions (:406-499) - pure NumPy methods, called
+    alg/alg_credit.py Alg.process_batch / process_actions (:406-499), the same methods of
+    alg_baseline*.py and alg_qmix*.py (which repeat different env-level fields per agent), and
+    Alg.process_goals / process_global_state (:501-557) - pure NumPy methods, called
     unbound on a stand-in `self` that carries the dimension attributes they read.  The modules import
     TensorFlow 1.x at the top, which is absent here: an inert stub module named `tensorflow` satisfies
     the import (nothing of it is called by these two methods), the same way oracle/ref_shims.py
@@ -57,6 +59,41 @@ def load_alg_modules():
     import replay_buffer
     import replay_buffer_dual
     return alg_credit, alg_credit_checkers, replay_buffer, replay_buffer_dual
+
+
+def load_alg_variants():
+    """The other two algorithm families' modules (same stub): {name: (particle module, checkers module)}."""
+    load_alg_modules()
+    import alg_baseline
+    import alg_baseline_checkers
+    import alg_qmix
+    import alg_qmix_checkers
+    return {"baseline": (alg_baseline, alg_baseline_checkers), "qmix": (alg_qmix, alg_qmix_checkers)}
+
+
+def variant_outputs(fix, names, batch, alg_mods, attrs, state_key, l_state_one):
+    """Adds to `fix` (i) what the baseline / qmix families' process_batch return for the same batch - only the
+    arrays that differ from alg_credit*'s (asserted: nothing else does) - and (ii) the returns of
+    process_goals / process_global_state (identical code in all six classes, called on alg_credit*'s outputs)."""
+    credit = {k: fix["out_" + k] for k in names}
+    for alg, mod in alg_mods.items():
+        me = stand_in(mod.Alg, **attrs)
+        out = mod.Alg.process_batch(me, batch.copy())
+        assert len(out) == len(names)
+        for k, v in zip(names, out):
+            v = np.asarray(v)
+            if v.shape != credit[k].shape or not np.array_equal(v, credit[k]):
+                fix["out_%s_%s" % (alg, k)] = v
+    n = attrs["n_agents"]
+    me = types.SimpleNamespace(n_agents=n, l_goal=2, l_state_one_agent=l_state_one, l_state=n * l_state_one)
+    any_alg = next(iter(alg_mods.values())).Alg
+    n_steps = int(credit["n_steps"])
+    gs, go = any_alg.process_goals(me, credit["goals"], n_steps)
+    fix["out_goals_self"], fix["out_goals_others"] = np.asarray(gs), np.asarray(go)
+    for suffix in ("", "_next"):
+        one, others, state = any_alg.process_global_state(me, credit[state_key + suffix], n_steps)
+        fix["out_v_global_one_agent" + suffix], fix["out_v_global_others" + suffix], fix["out_state" + suffix] = \
+            np.asarray(one), np.asarray(others), np.asarray(state)
 
 
 def transition(fields):
@@ -110,6 +147,9 @@ def checkers_batch(ck, alg_mod, rb_mod):
              "actions_1hot", "actions_others_1hot", "reward", "reward_local", "state_env_next", "state_agents_next",
              "obs_others_next", "obs_self_t_next", "obs_self_v_next", "done", "goals"]
     fix = {"out_" + k: np.asarray(v) for k, v in zip(names, out)}
+    attrs = dict(experiment="checkers", n_agents=n, l_action=l_action, l_obs_others=2 * (n - 1),
+                 rows_obs=5, columns_obs=5, channels_obs=3, l_obs_self=4)
+    variant_outputs(fix, names, batch, {k: v[1] for k, v in load_alg_variants().items()}, attrs, "state_agents", 4)
     in_names = ["grid", "vec", "obs_others", "obs_self_t", "obs_self_v", "actions_prev", "actions", "reward", "local_rewards",
                 "grid_next", "vec_next", "obs_others_next", "obs_self_t_next", "obs_self_v_next", "done", "goals"]
     for j, k in enumerate(in_names):      # the 66 transitions in the order they were added
@@ -157,6 +197,8 @@ def particle_batch(MultiAgentEnv, scenarios, alg_mod):
     names = ["n_steps", "v_global", "obs_others", "v_local", "actions_1hot", "actions_others_1hot", "reward", "reward_local",
              "v_global_next", "obs_others_next", "v_local_next", "done", "goals"]
     fix = {"out_" + k: np.asarray(v) for k, v in zip(names, out)}
+    attrs = dict(experiment="particle", n_agents=n, l_action=l_action, l_obs_others=4 * (n - 1), l_obs=4)
+    variant_outputs(fix, names, batch, {k: v[0] for k, v in load_alg_variants().items()}, attrs, "v_global", 4)
     in_names = ["global_state", "obs_others", "obs_self", "actions", "reward", "reward_n", "global_state_next",
                 "obs_others_next", "obs_self_next", "done", "goals"]
     for j, k in enumerate(in_names):
