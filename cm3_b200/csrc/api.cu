@@ -162,7 +162,10 @@ int balance_waves(const void *kern, int threads, int smem, int nblocks) {
             const long waves = (nblocks + resident - 1) / resident;
             const long last = nblocks - (waves - 1) * resident;
             const int target = (int)((nblocks + waves * sms - 1) / (waves * sms));  // blocks per SM of equal waves
-            // rebalance when the last wave would be less than half full (CM3_BALANCE_FRAC overrides the 0.5)
+            // rebalance when the last wave would be less than half full (CM3_BALANCE_FRAC overrides the 0.5).
+            // A fuller last wave is better left alone: CK2's is 73 % full, and forcing it into two equal waves of
+            // 14 blocks per SM (CM3_BALANCE_FRAC=0.9) costs more in resident blocks than the tail returns -
+            // 0.988 -> 0.875 of the roofline at K = 3300, 0.93 -> 0.84 on a single 20-step launch (run r02n).
             static const double frac = [] { const char *v = getenv("CM3_BALANCE_FRAC"); return v ? atof(v) : 0.5; }();
             if ((double)last < frac * (double)resident && target < per_sm) {
                 // grow the request until the occupancy calculator agrees with the target

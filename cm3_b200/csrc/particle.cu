@@ -9,7 +9,7 @@
 //   MultiAgentEnv.step tail / reset   multiagent/environment.py:95-149
 //
 // Design:
-//  * one THREAD per env, a warp per 32 consecutive envs, one warp per block.  All N <= 4 agents
+//  * one THREAD per env, a warp per 32 consecutive envs, one warp per block.  All N <= 8 agents
 //    of an env live in the registers of one thread, so the all-pairs contact force, the collision
 //    penalty and the env-level reductions are plain register arithmetic: every pair is evaluated
 //    once (in the reference's pair order, core.py:145-154), there are no shuffles, and the
