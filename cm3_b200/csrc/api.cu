@@ -84,13 +84,32 @@ int chain_parts(int ntiles) {
     return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
 }
 
-int chain_early_mode(int dflt) {
+int chain_early_mode(const void *kern, int threads, int smem, int nblocks) {
     static const int forced = [] {
         const char *v = getenv("CM3_CHAIN_EARLY");
         return v ? atoi(v) : -1;
     }();
-    const int m = forced >= 0 ? forced : dflt;
-    return m < 0 ? 0 : m > 2 ? 2 : m;
+    if (forced >= 0) return forced > 2 ? 2 : forced;
+    // one resident wave -> 2, else 0 (params.cuh); the occupancy query is cached per (kernel, device, smem)
+    struct Entry { const void *kern; int dev, smem; long resident; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Entry &e : cache)
+            if (e.kern == kern && e.dev == dev && e.smem == smem) return nblocks <= e.resident ? 2 : 0;
+    }
+    int sms = 0, per_sm = 0;
+    long resident = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) == cudaSuccess)
+        resident = (long)per_sm * sms;
+    (void)cudaGetLastError();
+    std::lock_guard<std::mutex> lk(mu);
+    cache.push_back(Entry{kern, dev, smem, resident});
+    return nblocks <= resident ? 2 : 0;
 }
 
 // Off by default: measured slower than one env per thread (profiles/r02k_ab.txt, r02l_ab.txt)
@@ -515,7 +534,7 @@ int cm3_checkers_step_chained(cm3_checkers_t h, const cm3_checkers_state *st, co
     if (!st->sync) { set_error("step_chained needs state.sync (the per-tile chaining words)"); return CM3_ERR_BAD_ARG; }
     if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = 1; p.auto_reset = auto_reset ? 1 : 0; p.chained = 1;
-    p.early = chain_early_mode(h->cfg.n_agents == 1 ? 2 : 0);  // measured, profiles/r02p_ab.txt
+    p.early = -1;  // resolved per launch shape (params.cuh: chain_early_mode)
     p.actions = actions; p.seed = seed; p.t0 = t0;
     return ck_launch(h, p, stream);
 }
@@ -795,7 +814,7 @@ int cm3_particle_step_chained(cm3_particle_t h, const cm3_particle_state *st, co
     if (!st->sync) { set_error("step_chained needs state.sync (the per-tile chaining words)"); return CM3_ERR_BAD_ARG; }
     if ((rc = check_actions_alignment(actions, h->cfg.n_agents)) != CM3_OK) return rc;
     p.mode = 0; p.T = 1; p.auto_reset = auto_reset ? 1 : 0; p.chained = 1;
-    p.early = chain_early_mode(2);  // measured, profiles/r02p_ab.txt
+    p.early = -1;  // resolved per launch shape (params.cuh: chain_early_mode)
     p.actions = actions; p.seed = seed; p.t0 = t0;
     return pt_launch(h, p, stream);
 }

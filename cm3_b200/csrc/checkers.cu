@@ -593,8 +593,11 @@ static int launch_ck(const Geo &geo, const CkParams &p, cudaStream_t stream) {
     // multi-step launches: equal waves (common.cuh: balance_waves)
     const int smem_launch = (p.mode == kCkStep && p.T > 1) ? balance_waves((const void *)kern, kCkWarpsPerBlock * kWarp, smem, nblocks) : smem;
     const int parts = (p.chained && kCkWarpsPerBlock == 1) ? chain_parts(ntiles) : 1;
+    const int early = (p.chained && p.early < 0) ? chain_early_mode((const void *)kern, kCkWarpsPerBlock * kWarp, smem_launch, nblocks)
+                                                 : (p.early < 0 ? 0 : p.early);
     for (int i = 0; i < parts; ++i) {  // disjoint tile ranges; one grid unless chained (params.cuh: chain_parts)
         CkParams q = p;
+        q.early = early;
         q.tile0 = (int)((long long)nblocks * i / parts);
         const int n = (int)((long long)nblocks * (i + 1) / parts) - q.tile0;
         if (n > 0) CM3_CUDA(launch_kernel(kern, n, kCkWarpsPerBlock * kWarp, smem_launch, stream, pdl_enabled(), q));

@@ -122,15 +122,18 @@ bool pdl_enabled();  // programmatic dependent launch between consecutive step l
 // slower for every workload at 2, 3 and 4 parts (profiles/r02c_ab.txt: the extra launches cost more
 // than the overlap returns); CM3_CHAIN_PARTS=<n> re-enables it.
 int chain_parts(int ntiles);
-// Where a chained launch writes its compact state back and publishes its tile (CkParams::early).  The next
-// step's block of the same tile needs the state, not the outputs: storing the state and releasing the
-// ticket BEFORE the observation tiles are assembled and stored takes the whole output phase - and the
-// memory barrier of the release, which otherwise queues behind this block's own tile stores - off the
-// tile-to-tile dependency chain.  Measured at 65 536 envs (profiles/r02p_ab.txt), early = 2 against 0:
-// PA4 0.755 -> 0.778, PA3 0.687 -> 0.745, PM2 0.487 -> 0.54, CK1 0.681 -> 0.691, CK2 0.896 -> 0.878 (its
-// 1.7 waves per launch pipeline without it, and the early barrier only delays the tile stores); early = 1
-// (state before, publish after) is within noise of 0.  Defaults: 2 for the particle kernels and one-agent
-// Checkers, 0 for Checkers with several agents; CM3_CHAIN_EARLY=0|1|2 overrides.
-int chain_early_mode(int dflt);
+// Where a chained launch writes its compact state back and publishes its tile (CkParams::early; -1 = decided
+// at launch by chain_early_mode).  The next step's block of the same tile needs the state, not the outputs:
+// storing the state and releasing the ticket BEFORE the observation tiles are assembled and stored takes the
+// whole output phase - and the memory barrier of the release, which otherwise queues behind this block's own
+// tile stores - off the tile-to-tile dependency chain.  It pays exactly when the launch is ONE resident wave:
+// there the step time is the chain (every tile's next block is already resident, waiting for its ticket), e.g.
+// at 65 536 envs PA3 0.687 -> 0.745, PM2 0.487 -> 0.54, PA4 0.755 -> 0.778, and at 32 768 envs CK2 0.734 -> 0.866,
+// CK1 0.523 -> 0.691 (profiles/r02p_ab.txt, r02u_ab.txt).  With more blocks than resident slots the next block of
+// a tile is mostly waiting for a SLOT, which frees when a block has stored its outputs, and the early barrier only
+// delays those stores: CK2 0.896 -> 0.878 at 65 536 envs (1.7 waves), 0.781 -> 0.753 at 49 152, PA4 0.804 -> 0.785 at
+// 131 072.  Rule: 2 (state and release before the outputs) when blocks <= resident slots of the kernel, else 0;
+// CM3_CHAIN_EARLY=0|1|2 overrides (1 = state before, release after: within noise of 0).
+int chain_early_mode(const void *kern, int threads, int smem, int nblocks);
 
 }  // namespace cm3

@@ -530,8 +530,10 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
     // multi-step launches: equal waves (common.cuh: balance_waves)
     const int smem_launch = (p.mode == kPtStep && p.T > 1) ? balance_waves((const void *)kern, kWarp, kSmem, nblocks) : kSmem;
     const int parts = p.chained ? chain_parts(nblocks) : 1;
+    const int early = (p.chained && p.early < 0) ? chain_early_mode((const void *)kern, kWarp, smem_launch, nblocks) : (p.early < 0 ? 0 : p.early);
     for (int i = 0; i < parts; ++i) {  // disjoint tile ranges; one grid unless chained (params.cuh: chain_parts)
         PtParams q = p;
+        q.early = early;
         q.tile0 = (int)((long long)nblocks * i / parts);
         const int n = (int)((long long)nblocks * (i + 1) / parts) - q.tile0;
         if (n > 0) CM3_CUDA(launch_kernel(kern, n, kWarp, smem_launch, stream, pdl_enabled(), q));
