@@ -84,13 +84,8 @@ int chain_parts(int ntiles) {
     return ntiles >= 296 * parts ? parts : 1;   // keep at least two blocks per SM in every partial grid
 }
 
-int chain_early_mode(const void *kern, int threads, int smem, int nblocks) {
-    static const int forced = [] {
-        const char *v = getenv("CM3_CHAIN_EARLY");
-        return v ? atoi(v) : -1;
-    }();
-    if (forced >= 0) return forced > 2 ? 2 : forced;
-    // one resident wave -> 2, else 0 (params.cuh); the occupancy query is cached per (kernel, device, smem)
+// resident blocks of `kern` on the current device (occupancy query, cached per (kernel, device, smem)); 0 on failure
+static long resident_slots(const void *kern, int threads, int smem) {
     struct Entry { const void *kern; int dev, smem; long resident; };
     static std::mutex mu;
     static std::vector<Entry> cache;
@@ -99,7 +94,7 @@ int chain_early_mode(const void *kern, int threads, int smem, int nblocks) {
     {
         std::lock_guard<std::mutex> lk(mu);
         for (const Entry &e : cache)
-            if (e.kern == kern && e.dev == dev && e.smem == smem) return nblocks <= e.resident ? 2 : 0;
+            if (e.kern == kern && e.dev == dev && e.smem == smem) return e.resident;
     }
     int sms = 0, per_sm = 0;
     long resident = 0;
@@ -109,7 +104,26 @@ int chain_early_mode(const void *kern, int threads, int smem, int nblocks) {
     (void)cudaGetLastError();
     std::lock_guard<std::mutex> lk(mu);
     cache.push_back(Entry{kern, dev, smem, resident});
-    return nblocks <= resident ? 2 : 0;
+    return resident;
+}
+
+int chain_early_mode(const void *kern, int threads, int smem, int nblocks) {
+    static const int forced = [] {
+        const char *v = getenv("CM3_CHAIN_EARLY");
+        return v ? atoi(v) : -1;
+    }();
+    if (forced >= 0) return forced > 2 ? 2 : forced;
+    return nblocks <= resident_slots(kern, threads, smem) ? 2 : 0;  // one resident wave -> 2, else 0 (params.cuh)
+}
+
+int chain_tiles_per_block(const void *kern, int threads, int smem, int nblocks) {
+    static const int forced = [] {
+        const char *v = getenv("CM3_CHAIN_TPB");
+        return v ? atoi(v) : 0;
+    }();
+    if (forced > 0) return forced >= 2 ? 2 : 1;
+    const long resident = resident_slots(kern, threads, smem);
+    return (resident > 0 && nblocks > resident && (nblocks + 1) / 2 <= resident) ? 2 : 1;
 }
 
 // Off by default: measured slower than one env per thread (profiles/r02k_ab.txt, r02l_ab.txt)
