@@ -137,8 +137,8 @@ int chain_parts(int ntiles);
 // CM3_CHAIN_EARLY=0|1|2 overrides (1 = state before, release after: within noise of 0).
 int chain_early_mode(const void *kern, int threads, int smem, int nblocks);
 // Tiles per block (1 or 2) of a chained single-step launch of `nblocks` one-tile blocks: 2 when the launch does not
-// fit the kernel's resident slots but half as many two-tile blocks do - it then runs as ONE resident wave and the
-// early release applies.  CM3_CHAIN_TPB=1|2 forces a value.
+// fit the kernel's resident slots (with half as many two-tile blocks it often runs as ONE resident wave, and then
+// the early release applies).  CM3_CHAIN_TPB=1|2 forces a value.
 int chain_tiles_per_block(const void *kern, int threads, int smem, int nblocks);
 
 }  // namespace cm3
