@@ -106,6 +106,36 @@ def test_chained_steps_equal_stream_ordered_steps(game, B):
             assert torch.equal(slots[f], want[f][:ring]), (game, f)
 
 
+@pytest.mark.parametrize("game,B", [("ck2", 40008), ("ck1", 60000)])
+def test_chained_launches_with_two_tiles_per_block(game, B):
+    """A chained Checkers launch with more tiles than resident slots gives every block two tiles (checkers.cu:
+    launch_ck / step_tile; 40 008 envs x 2 agents = 2501 tiles, 60 000 envs x 1 agent = 3750 tiles, ragged last
+    tile): a CUDA graph of such launches, replayed twice, equals plain stream-ordered steps in every field and
+    leaves the same state."""
+    from cm3_b200.graph import ChainedStepGraph
+    ring = 12
+    rng = np.random.default_rng(B)
+
+    def make():
+        e = VecCheckers(B, **(CK2 if game == "ck2" else CK1))
+        e.reset(goals=np.eye(2) if game == "ck2" else np.array([[0, 1]]))
+        return e
+    c, d = make(), make()
+    actions = torch.from_numpy(rng.integers(0, 5, size=(ring, B, c.N)).astype(np.int8)).to(c.device)
+    slots = c.alloc_outputs(ring, fields=CK_REF)
+    g = ChainedStepGraph(c, actions, slots, seed=5, t0=0, auto_reset=True)
+    ref = d.alloc_outputs(ring, fields=CK_REF)
+    for rep in range(2):
+        g.replay()
+        for t in range(ring):
+            d.rollout(1, actions=actions[t:t + 1], auto_reset=True, out={k: v[t:t + 1] for k, v in ref.items()})
+        torch.cuda.synchronize()
+        for f in CK_REF:
+            assert torch.equal(slots[f], ref[f]), (game, "replay %d" % rep, f)
+    for k in c.state:
+        assert torch.equal(c.state[k], d.state[k]), k
+
+
 def test_chained_needs_sync_words():
     import ctypes as C
     from cm3_b200 import _lib as L
