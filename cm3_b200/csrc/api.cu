@@ -121,13 +121,12 @@ int chain_tiles_per_block(const void *kern, int threads, int smem, int nblocks) 
         const char *v = getenv("CM3_CHAIN_TPB");
         return v ? atoi(v) : 0;
     }();
-    if (forced > 0) return forced >= 2 ? 2 : 1;
+    if (forced > 0) return forced > 4 ? 4 : forced;
+    // as many tiles per block as it takes to make the launch one resident wave, at most 4 (params.cuh)
     const long resident = resident_slots(kern, threads, smem);
-    // two tiles per block whenever the launch does not fit the resident slots: where that makes it one wave the early
-    // release applies (CK1 at 65 536 envs 0.67 -> 0.75), and beyond it still halves the blocks that queue for a slot
-    // (CK2 at 131 072 envs 0.79 -> 0.83).  Four tiles per block were measured much slower (0.69 / 0.59 at 65 536):
-    // the tiles of a block are stepped one after the other, and that serial chain then outweighs the slots it frees.
-    return (resident > 0 && nblocks > resident) ? 2 : 1;
+    if (resident <= 0 || nblocks <= resident) return 1;
+    const long tpb = (nblocks + resident - 1) / resident;
+    return tpb > 4 ? 4 : (int)tpb;
 }
 
 // Off by default: measured slower than one env per thread (profiles/r02k_ab.txt, r02l_ab.txt)

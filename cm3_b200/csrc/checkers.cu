@@ -199,32 +199,39 @@ checkers_kernel(const __grid_constant__ CkParams p) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool leader = elect_one();  // issues, commits and waits for this warp's bulk stores (common.cuh)
-    // A block normally owns one tile per warp.  A chained single-step launch with more tiles than resident slots (but at
-    // most twice as many) gives every block TWO tiles instead, one grid stride apart, which it steps one after the other:
-    // the launch is then a single resident wave, the next launch's blocks are all resident behind it, and no tile waits
-    // for a slot (launch_ck).
+    // A block normally owns one tile per warp.  A chained single-step launch with more tiles than resident slots
+    // gives every block p.tpb (2..4) tiles instead, one grid stride apart, which it steps one after the other: the
+    // launch is then a single resident wave (or as close to one as four tiles per block get it), the early release
+    // applies, and fewer blocks queue for a slot (launch_ck).
     const int tile_first = p.tile0 + blockIdx.x * kCkWarpsPerBlock + warp;
     const int tile_stride = (int)gridDim.x * kCkWarpsPerBlock;
-    const int n_my_tiles = p.tpb > 1 ? 2 : 1;
+    const int n_my_tiles = p.tpb > 1 ? p.tpb : 1;
     // launch chaining: the tickets of ALL my tiles are taken BEFORE the next grid may be scheduled (common.cuh)
     // (0xFFFFFFFF = not taken: neutral in the AND below, which must depend on every atomic that WAS issued)
-    uint32_t mine0 = 0xFFFFFFFFu, mine1 = 0xFFFFFFFFu;
+    uint32_t mine0 = 0xFFFFFFFFu, mine1 = 0xFFFFFFFFu, mine2 = 0xFFFFFFFFu, mine3 = 0xFFFFFFFFu;
     if (p.sync != nullptr) {
-        // both atomics in flight together (lane 0), then one broadcast each
-        const int t1 = tile_first + tile_stride;
-        const bool h0 = tile_first * EW < p.B, h1 = n_my_tiles > 1 && t1 * EW < p.B;
+        // all atomics in flight together (lane 0), then one broadcast each
+        const int t1 = tile_first + tile_stride, t2 = t1 + tile_stride, t3 = t2 + tile_stride;
+        const bool h0 = tile_first * EW < p.B, h1 = n_my_tiles > 1 && t1 * EW < p.B, h2 = n_my_tiles > 2 && t2 * EW < p.B,
+                   h3 = n_my_tiles > 3 && t3 * EW < p.B;
         if (lane == 0) {
             if (h0) mine0 = atomicAdd(p.sync + 2 * (size_t)tile_first, 1u);
             if (h1) mine1 = atomicAdd(p.sync + 2 * (size_t)t1, 1u);
+            if (h2) mine2 = atomicAdd(p.sync + 2 * (size_t)t2, 1u);
+            if (h3) mine3 = atomicAdd(p.sync + 2 * (size_t)t3, 1u);
         }
         mine0 = __shfl_sync(0xFFFFFFFFu, mine0, 0);
-        if (n_my_tiles > 1) mine1 = __shfl_sync(0xFFFFFFFFu, mine1, 0);
+        if (n_my_tiles > 1) {
+            mine1 = __shfl_sync(0xFFFFFFFFu, mine1, 0);
+            mine2 = __shfl_sync(0xFFFFFFFFu, mine2, 0);
+            mine3 = __shfl_sync(0xFFFFFFFFu, mine3, 0);
+        }
     } else {
         mine0 = 0;  // no chaining words: trigger at once
     }
     // the trigger is issued under a branch on the returned tickets: every atomic has been performed at L2 before
     // any block of the next grid can take its own (a ticket never reaches 0xFFFFFFFF: the chain traps long before)
-    if ((mine0 & mine1) != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
+    if ((mine0 & mine1 & mine2 & mine3) != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *lut_row = reinterpret_cast<Real *>(smem_raw);
@@ -239,14 +246,15 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     Tile *stage_win = reinterpret_cast<Tile *>(smem_raw + Ly::lut_bytes(geo) + warp * Ly::warp_stage_bytes(geo));
     Tile *stage_grid = reinterpret_cast<Tile *>(reinterpret_cast<unsigned char *>(stage_win) + win_bytes);
 
-    // one tile, start to finish (inlined once per tile of the block: straight-line copies, not a loop - see launch_ck)
-    auto step_tile = [&](const int tile, const uint32_t my_ticket) __attribute__((always_inline)) {
+#pragma unroll 1
+    for (int my = 0; my < n_my_tiles; ++my) {
+    const int tile = tile_first + my * tile_stride;
     const int env0 = tile * EW;
-    if (env0 >= p.B) return;  // warp-uniform; no block-level sync below this point
+    if (env0 >= p.B) return;  // warp-uniform; no block-level sync below this point (later tiles of mine lie further out)
     TileTicket ticket;
     ticket.on = p.sync != nullptr;
     ticket.w = p.sync + 2 * (size_t)tile;
-    ticket.mine = my_ticket;
+    ticket.mine = my == 0 ? mine0 : my == 1 ? mine1 : my == 2 ? mine2 : mine3;
     const int a = lane / EW, e = lane % EW;  // agent-major: lanes [a*EW, (a+1)*EW) hold agent a
     const int env = env0 + e;
     const int nenv = min(EW, p.B - env0);
@@ -587,6 +595,12 @@ checkers_kernel(const __grid_constant__ CkParams p) {
         // launches, params.cuh: chain_early_mode) writes it back - and, at 2, releases the tile - before the
         // tiles of the last step are expanded and stored.
         if (p.early != 0 && t == T_eff - 1) {
+            // Every lane of an env loaded the env's state for itself, and lane a == 0 is about to overwrite it: all
+            // those loads must have been performed first.  Nothing else orders them - the lanes of a warp need not
+            // run in step behind the spin-wait (a __syncwarp is a barrier, not a promise of lockstep), and with the
+            // store this early the one lane that polled was seen to finish its step and store before the others
+            // had loaded (outputs of the tile's first env one action ahead, profiles/r02u_ab.txt (5)).
+            __syncwarp();
             store_state();
             if (p.early == 2) ticket.publish(lane);
         }
@@ -599,9 +613,7 @@ checkers_kernel(const __grid_constant__ CkParams p) {
     // smem must outlive the async reads (and be free for my next tile); the global writes themselves complete with the grid
     if (pending && leader) bulk_wait_read();
     __syncwarp();
-    };  // step_tile
-    step_tile(tile_first, mine0);
-    if (n_my_tiles > 1) step_tile(tile_first + tile_stride, mine1);
+    }  // my tiles
 }
 
 // ------------------------------------------------------------------------ host side
@@ -625,7 +637,7 @@ static int launch_ck(const Geo &geo, const CkParams &p, cudaStream_t stream) {
     const int smem_launch = (p.mode == kCkStep && p.T > 1) ? balance_waves((const void *)kern, kCkWarpsPerBlock * kWarp, smem, nblocks) : smem;
     const int parts = (p.chained && kCkWarpsPerBlock == 1) ? chain_parts(ntiles) : 1;
     // chained single-step launches: as many tiles per block as it takes to make the launch one resident wave
-    // (at most 2; params.cuh: chain_tiles_per_block), then the early release applies
+    // (at most 4; params.cuh: chain_tiles_per_block), then the early release applies
     const int tpb = (p.chained && p.T == 1 && parts == 1 && kCkWarpsPerBlock == 1)
                         ? chain_tiles_per_block((const void *)kern, kWarp, smem_launch, nblocks) : 1;
     const int grid_blocks = (nblocks + tpb - 1) / tpb;

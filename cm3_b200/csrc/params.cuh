@@ -45,7 +45,7 @@ struct CkParams {
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
     int chained;      // 1: wait for this tile's predecessor only (TileTicket) instead of griddepcontrol.wait
-    int tpb;          // 2: every block of this chained single-step launch steps two tiles (checkers.cu: launch_ck)
+    int tpb;          // tiles per block of a chained single-step launch (0 / 1: one; checkers.cu: launch_ck)
     int early;        // when the compact state of the launch's LAST step is written back and the tile published
                       // (params.cuh: chain_early_mode): 0 after the step's outputs, 1 state before / publish after,
                       // 2 both before the outputs are assembled
@@ -136,9 +136,10 @@ int chain_parts(int ntiles);
 // 131 072.  Rule: 2 (state and release before the outputs) when blocks <= resident slots of the kernel, else 0;
 // CM3_CHAIN_EARLY=0|1|2 overrides (1 = state before, release after: within noise of 0).
 int chain_early_mode(const void *kern, int threads, int smem, int nblocks);
-// Tiles per block (1 or 2) of a chained single-step launch of `nblocks` one-tile blocks: 2 when the launch does not
-// fit the kernel's resident slots (with half as many two-tile blocks it often runs as ONE resident wave, and then
-// the early release applies).  CM3_CHAIN_TPB=1|2 forces a value.
+// Tiles per block of a chained single-step launch of `nblocks` one-tile blocks: as many as it takes to make the launch
+// ONE resident wave - ceil(nblocks / resident slots), at most 4 - so that the early release applies and fewer blocks
+// queue for a slot; 1 when it fits anyway.  A block steps its tiles one after the other (a loop around the tile body).
+// CM3_CHAIN_TPB=1..4 forces a value (4 where 2 would do is much slower: the serial chain inside a block).
 int chain_tiles_per_block(const void *kern, int threads, int smem, int nblocks);
 
 }  // namespace cm3

@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
         // launches, params.cuh: chain_early_mode) writes it back - and, at 2, releases the tile - before the
         // observation tiles of the last step are assembled and stored.
         if (p.early != 0 && t == T_eff - 1) {
+            // (no warp barrier needed here, unlike checkers.cu: a lane loads and stores the state of ITS env only)
             store_state();
             if (p.early == 2) ticket.publish(lane);
         }
