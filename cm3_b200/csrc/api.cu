@@ -129,6 +129,22 @@ int chain_tiles_per_block(const void *kern, int threads, int smem, int nblocks) 
     return tpb > 4 ? 4 : (int)tpb;
 }
 
+int particle_chain_tpb(const void *kern, int threads, int smem, int nblocks) {
+    static const int forced = [] {
+        const char *v = getenv("CM3_PT_TPB");
+        return v ? atoi(v) : 0;
+    }();
+    if (forced > 0) {
+        const int t = forced > 4 ? 4 : forced;
+        return nblocks >= 2 * t ? t : 1;
+    }
+    // the one-wave rule of the Checkers launches (multi-wave batches: 131 072 envs and more)
+    const long resident = resident_slots(kern, threads, smem);
+    if (resident <= 0 || nblocks <= resident) return 1;
+    const long tpb = (nblocks + resident - 1) / resident;
+    return tpb > 4 ? 4 : (int)tpb;
+}
+
 // Off by default: measured slower than one env per thread (profiles/r02k_ab.txt, r02l_ab.txt)
 bool duo_enabled() {
     static const bool on = [] {

@@ -84,7 +84,7 @@ struct PtParams {
     int n_dst;
     long long out_B, out_env0;
     int B, T, max_steps, mode, auto_reset;
-    int chained, tile0, early;  // see CkParams
+    int chained, tile0, early, tpb;  // see CkParams
     unsigned long long seed;
     long long t0, env_id_offset, reset_counter;
     double dt, damping, contact_force, contact_margin, dist_min, mass, sensitivity, reach_thresh;
@@ -141,5 +141,9 @@ int chain_early_mode(const void *kern, int threads, int smem, int nblocks);
 // queue for a slot; 1 when it fits anyway.  A block steps its tiles one after the other (a loop around the tile body).
 // CM3_CHAIN_TPB=1..4 forces a value (4 where 2 would do is much slower: the serial chain inside a block).
 int chain_tiles_per_block(const void *kern, int threads, int smem, int nblocks);
+// The same for the particle kernels.  Their headline launch already is one wave (2048 blocks on 2368 slots), so the rule
+// above gives 1 there; CM3_PT_TPB=<n> forces n tiles per block whenever the launch has at least 2 n blocks (experiment:
+// half as many blocks would let two consecutive launches be resident together).
+int particle_chain_tpb(const void *kern, int threads, int smem, int nblocks);
 
 }  // namespace cm3

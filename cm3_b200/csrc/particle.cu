@@ -86,17 +86,50 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
 
     const int lane = threadIdx.x;
     const bool leader = elect_one();  // issues, commits and waits for this warp's TMA stores (common.cuh)
-    // launch chaining: the ticket is taken BEFORE the next grid may be scheduled (common.cuh)
-    TileTicket ticket;
-    const int tile = p.tile0 + (int)blockIdx.x;
-    ticket.take(p.sync, tile, lane);
-    if (ticket.mine != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
+    // A block normally owns one tile.  A chained single-step launch may give every block p.tpb (2..4) tiles instead, one
+    // grid stride apart, stepped one after the other (launch_pt; as in checkers.cu).
+    const int tile_first = p.tile0 + (int)blockIdx.x;
+    const int tile_stride = (int)gridDim.x;
+    const int n_my_tiles = p.tpb > 1 ? p.tpb : 1;
+    // launch chaining: the tickets of ALL my tiles are taken BEFORE the next grid may be scheduled (common.cuh)
+    // (0xFFFFFFFF = not taken: neutral in the AND below, which must depend on every atomic that WAS issued)
+    uint32_t mine0 = 0xFFFFFFFFu, mine1 = 0xFFFFFFFFu, mine2 = 0xFFFFFFFFu, mine3 = 0xFFFFFFFFu;
+    if (p.sync != nullptr) {
+        const int t1 = tile_first + tile_stride, t2 = t1 + tile_stride, t3 = t2 + tile_stride;
+        const bool h0 = tile_first * kWarp < p.B, h1 = n_my_tiles > 1 && t1 * kWarp < p.B, h2 = n_my_tiles > 2 && t2 * kWarp < p.B,
+                   h3 = n_my_tiles > 3 && t3 * kWarp < p.B;
+        if (lane == 0) {  // all atomics in flight together, then one broadcast each
+            if (h0) mine0 = atomicAdd(p.sync + 2 * (size_t)tile_first, 1u);
+            if (h1) mine1 = atomicAdd(p.sync + 2 * (size_t)t1, 1u);
+            if (h2) mine2 = atomicAdd(p.sync + 2 * (size_t)t2, 1u);
+            if (h3) mine3 = atomicAdd(p.sync + 2 * (size_t)t3, 1u);
+        }
+        mine0 = __shfl_sync(0xFFFFFFFFu, mine0, 0);
+        if (n_my_tiles > 1) {
+            mine1 = __shfl_sync(0xFFFFFFFFu, mine1, 0);
+            mine2 = __shfl_sync(0xFFFFFFFFu, mine2, 0);
+            mine3 = __shfl_sync(0xFFFFFFFFu, mine3, 0);
+        }
+    } else {
+        mine0 = 0;  // no chaining words: trigger at once
+    }
+    // the trigger is issued under a branch on the returned tickets: every atomic has been performed at L2 before any
+    // block of the next grid can take its own
+    if ((mine0 & mine1 & mine2 & mine3) != 0xFFFFFFFFu) pdl_launch_dependents();  // the next step's grid may become resident while this one drains
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *stage_base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
     const bool reset_mode = !FULL && p.mode == kPtReset;
+#pragma unroll 1
+    for (int my = 0; my < n_my_tiles; ++my) {
+    const int tile = tile_first + my * tile_stride;
     const int env0 = tile * kWarp;
+    if (env0 >= p.B) return;  // warp-uniform (one warp per block); later tiles of mine lie further out
+    TileTicket ticket;
+    ticket.on = p.sync != nullptr;
+    ticket.w = p.sync + 2 * (size_t)tile;
+    ticket.mine = my == 0 ? mine0 : my == 1 ? mine1 : my == 2 ? mine2 : mine3;
     const int env = env0 + lane;
     const int nenv = FULL ? kWarp : min(kWarp, p.B - env0);
     const bool valid = FULL || lane < nenv;
@@ -488,8 +521,10 @@ __global__ void __launch_bounds__(kWarp, pt_min_blocks(N)) particle_kernel(const
 
     if (p.early == 0 || T_eff < 1) store_state();
     if (p.early != 2 || T_eff < 1) ticket.publish(lane);  // this tile's next launch may go ahead
-    // shared memory must outlive the async reads; the global writes themselves complete with the grid
+    // shared memory must outlive the async reads (and be free for my next tile); the global writes themselves complete with the grid
     if (pending && leader) bulk_wait_read();
+    __syncwarp();
+    }  // my tiles
 }
 
 // ------------------------------------------------------------------------ host side
@@ -531,12 +566,16 @@ static int launch_pt(const PtParams &p, cudaStream_t stream) {
     // multi-step launches: equal waves (common.cuh: balance_waves)
     const int smem_launch = (p.mode == kPtStep && p.T > 1) ? balance_waves((const void *)kern, kWarp, kSmem, nblocks) : kSmem;
     const int parts = p.chained ? chain_parts(nblocks) : 1;
-    const int early = (p.chained && p.early < 0) ? chain_early_mode((const void *)kern, kWarp, smem_launch, nblocks) : (p.early < 0 ? 0 : p.early);
+    // chained single-step launches may step several tiles per block (params.cuh: chain_tiles_per_block; CM3_PT_TPB)
+    const int tpb = (p.chained && p.T == 1 && parts == 1) ? particle_chain_tpb((const void *)kern, kWarp, smem_launch, nblocks) : 1;
+    const int grid_blocks = (nblocks + tpb - 1) / tpb;
+    const int early = (p.chained && p.early < 0) ? chain_early_mode((const void *)kern, kWarp, smem_launch, grid_blocks) : (p.early < 0 ? 0 : p.early);
     for (int i = 0; i < parts; ++i) {  // disjoint tile ranges; one grid unless chained (params.cuh: chain_parts)
         PtParams q = p;
         q.early = early;
-        q.tile0 = (int)((long long)nblocks * i / parts);
-        const int n = (int)((long long)nblocks * (i + 1) / parts) - q.tile0;
+        q.tpb = tpb;
+        q.tile0 = (int)((long long)grid_blocks * i / parts);
+        const int n = (int)((long long)grid_blocks * (i + 1) / parts) - q.tile0;
         if (n > 0) CM3_CUDA(launch_kernel(kern, n, kWarp, smem_launch, stream, pdl_enabled(), q));
     }
     return CM3_OK;
