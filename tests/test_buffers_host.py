@@ -43,3 +43,19 @@ def test_host_actions_are_saturated_and_int8_passes_through():
     np.testing.assert_array_equal(_to_int8_host(a, (2, 2)), np.array([[0, 4], [127, -128]], dtype=np.int8))
     b = np.arange(4, dtype=np.int8)
     assert np.shares_memory(_to_int8_host(b, (2, 2)), b)
+
+
+def test_bind_host_to_gpu_is_a_no_op_without_nvml_or_when_disabled(monkeypatch):
+    """cm3_b200.sharding.bind_host_to_gpu: an optimisation for multi-socket hosts, never a requirement - without a
+    driver (this container) or with CM3_BIND_NUMA=0 it returns 0 and leaves the affinity mask alone."""
+    import os
+    from cm3_b200.sharding import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("CM3_BIND_NUMA", "0")
+    assert bind_host_to_gpu(0) == 0
+    monkeypatch.delenv("CM3_BIND_NUMA")
+    n = bind_host_to_gpu(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
